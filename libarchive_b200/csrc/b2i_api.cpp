@@ -1,0 +1,533 @@
+/*
+ * b2i_api.cpp — the C ABI of include/b200inflate.h over the sm_100a kernels.
+ *
+ * Host side of "the host batches entry offsets up front, launches one device
+ * pass and serves archive_read_data from the decoded buffers": a plan is the
+ * batch (descriptors + schedule, uploaded once), a launch is the device pass.
+ * There is no CPU decode path in this library: without a usable sm_100 device
+ * every entry point fails with B2I_E_NODEVICE.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/b200inflate.h"
+#include "b2i_kernels.h"
+
+static_assert(sizeof(b2i_stream_desc) == sizeof(B2iDesc), "descriptor layout");
+static_assert(sizeof(b2i_stream_result) == sizeof(B2iResult), "result layout");
+static_assert(offsetof(b2i_stream_desc, expect_crc) == offsetof(B2iDesc, expect_crc), "descriptor layout");
+static_assert(offsetof(b2i_stream_result, detail) == offsetof(B2iResult, detail), "result layout");
+
+/* per-stream limits of this build: 32-bit positions inside one stream */
+#define B2I_MAX_STREAM_BYTES 0xFFFF0000ull
+
+struct b2i_ctx {
+	int device;
+	int num_sms;
+	cudaStream_t stream;
+	bool own_stream;
+	uint32_t *d_crc_tab;   /* 1024 */
+	uint32_t *d_xp8;       /* 40 */
+	uint64_t launches;
+	/* grow-only staging for b2i_decode_host / b2i_crc32 */
+	uint8_t *d_in;  size_t d_in_cap;
+	uint8_t *d_out; size_t d_out_cap;
+	char err[256];
+};
+
+struct b2i_plan {
+	b2i_ctx *ctx;
+	size_t n;
+	uint32_t n_deflate, n_stored, n_work, n_unsup;
+	bool need_aligned_in;
+	uint64_t max_in_end, max_out_end;
+	/* device */
+	uint8_t *d_block;
+	B2iDesc *d_descs;
+	B2iResult *d_results;
+	uint32_t *d_order;
+	B2iCrcWork *d_work;
+	B2iCrcEntry *d_ents;
+	uint32_t *d_partial;
+	uint32_t *d_unsup;
+	unsigned int *d_counter;
+	/* pinned host mirror used for upload and result download */
+	uint8_t *h_block;
+	size_t block_bytes, results_off;
+};
+
+static int fail(b2i_ctx *c, int code, const char *fmt, ...)
+{
+	if (c) {
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(c->err, sizeof(c->err), fmt, ap);
+		va_end(ap);
+	}
+	return code;
+}
+
+#define CU(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return fail((c), B2I_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+extern "C" int b2i_abi_version(void) { return B2I_ABI_VERSION; }
+
+extern "C" int b2i_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess)
+		return 0;
+	return n;
+}
+
+extern "C" int b2i_ctx_create(int device, void *cuda_stream, b2i_ctx **out)
+{
+	if (out == NULL)
+		return B2I_E_INVAL;
+	*out = NULL;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+		return B2I_E_NODEVICE;
+	int major = 0, sms = 0;
+	if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+	    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+		return B2I_E_NODEVICE;
+	if (major != 10)
+		return B2I_E_NODEVICE;      /* kernels are sm_100a only; no fallback */
+	b2i_ctx *c = new (std::nothrow) b2i_ctx();
+	if (c == NULL)
+		return B2I_E_NOMEM;
+	memset(c, 0, sizeof(*c));
+	c->device = device;
+	c->num_sms = sms;
+	if (cudaSetDevice(device) != cudaSuccess) {
+		delete c;
+		return B2I_E_CUDA;
+	}
+	if (cuda_stream) {
+		c->stream = (cudaStream_t)cuda_stream;
+	} else {
+		if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+			delete c;
+			return B2I_E_CUDA;
+		}
+		c->own_stream = true;
+	}
+	if (cudaMalloc(&c->d_crc_tab, 1024 * 4) != cudaSuccess ||
+	    cudaMalloc(&c->d_xp8, 40 * 4) != cudaSuccess ||
+	    b2i_launch_tables(c->d_crc_tab, c->d_xp8, c->stream) != cudaSuccess ||
+	    cudaStreamSynchronize(c->stream) != cudaSuccess) {
+		b2i_ctx_destroy(c);
+		return B2I_E_CUDA;
+	}
+	c->launches = 1;
+	*out = c;
+	return B2I_OK;
+}
+
+extern "C" void b2i_ctx_destroy(b2i_ctx *c)
+{
+	if (c == NULL)
+		return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	cudaFree(c->d_crc_tab);
+	cudaFree(c->d_xp8);
+	cudaFree(c->d_in);
+	cudaFree(c->d_out);
+	if (c->own_stream)
+		cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" const char *b2i_last_error(const b2i_ctx *c) { return c ? c->err : "no context"; }
+extern "C" uint64_t b2i_ctx_launch_count(const b2i_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int b2i_ctx_sync(b2i_ctx *c)
+{
+	if (c == NULL)
+		return B2I_E_INVAL;
+	CU(c, cudaStreamSynchronize(c->stream));
+	return B2I_OK;
+}
+
+extern "C" void *b2i_host_alloc(size_t bytes)
+{
+	void *p = NULL;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+		return NULL;
+	return p;
+}
+extern "C" void b2i_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void *b2i_device_alloc(b2i_ctx *c, size_t bytes)
+{
+	void *p = NULL;
+	if (c == NULL || cudaSetDevice(c->device) != cudaSuccess)
+		return NULL;
+	/* +16: the input ring reads whole 16-byte units */
+	if (cudaMalloc(&p, ((bytes + 15) & ~(size_t)15) + 16) != cudaSuccess)
+		return NULL;
+	return p;
+}
+extern "C" void b2i_device_free(b2i_ctx *c, void *p) { if (c && p) { cudaSetDevice(c->device); cudaFree(p); } }
+
+extern "C" int b2i_memcpy_h2d(b2i_ctx *c, void *dst, const void *src, size_t bytes)
+{
+	if (c == NULL)
+		return B2I_E_INVAL;
+	CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+	return B2I_OK;
+}
+extern "C" int b2i_memcpy_d2h(b2i_ctx *c, void *dst, const void *src, size_t bytes)
+{
+	if (c == NULL)
+		return B2I_E_INVAL;
+	CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+	return B2I_OK;
+}
+
+/* ---- plan ------------------------------------------------------------------ */
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+
+extern "C" int b2i_plan_create(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, b2i_plan **out)
+{
+	if (c == NULL || out == NULL || (n && descs == NULL) || n > 0x7fffffffu)
+		return fail(c, B2I_E_INVAL, "b2i_plan_create: bad arguments");
+	*out = NULL;
+	CU(c, cudaSetDevice(c->device));
+
+	std::vector<uint32_t> deflate, unsup;
+	std::vector<B2iCrcWork> work;
+	std::vector<B2iCrcEntry> ents;
+	uint64_t max_in = 0, max_out = 0;
+	for (size_t i = 0; i < n; i++) {
+		const b2i_stream_desc &d = descs[i];
+		if (d.out_off & 15)
+			return fail(c, B2I_E_INVAL, "stream %zu: out_off must be a multiple of 16", i);
+		if (d.in_off + d.in_len < d.in_off || d.out_off + d.out_cap < d.out_off)
+			return fail(c, B2I_E_INVAL, "stream %zu: offset overflow", i);
+		if (d.method == B2I_METHOD_DEFLATE) {
+			if (d.in_len > B2I_MAX_STREAM_BYTES || d.out_cap > B2I_MAX_STREAM_BYTES)
+				return fail(c, B2I_E_INVAL, "stream %zu: larger than this build's 4 GiB per-stream limit", i);
+			deflate.push_back((uint32_t)i);
+			max_in = std::max<uint64_t>(max_in, d.in_off + d.in_len);
+			max_out = std::max<uint64_t>(max_out, d.out_off + d.out_cap);
+		} else if (d.method == B2I_METHOD_STORED) {
+			B2iCrcEntry e;
+			e.entry = (uint32_t)i;
+			e.first_work = (uint32_t)work.size();
+			e.pad = 0;
+			for (uint64_t rel = 0; rel < d.in_len; rel += B2I_CRC_CHUNK) {
+				B2iCrcWork w;
+				w.rel = rel;
+				w.len = (uint32_t)std::min<uint64_t>(B2I_CRC_CHUNK, d.in_len - rel);
+				w.entry = (uint32_t)i;
+				work.push_back(w);
+			}
+			e.nwork = (uint32_t)work.size() - e.first_work;
+			ents.push_back(e);
+			max_in = std::max<uint64_t>(max_in, d.in_off + d.in_len);
+			if (!(d.flags & B2I_F_NO_COPY))
+				max_out = std::max<uint64_t>(max_out, d.out_off + std::min(d.in_len, d.out_cap));
+		} else {
+			unsup.push_back((uint32_t)i);
+		}
+	}
+	/* largest streams first: the slowest warp starts earliest */
+	std::stable_sort(deflate.begin(), deflate.end(), [&](uint32_t a, uint32_t b) {
+		return descs[a].in_len + descs[a].out_cap > descs[b].in_len + descs[b].out_cap;
+	});
+
+	b2i_plan *p = new (std::nothrow) b2i_plan();
+	if (p == NULL)
+		return fail(c, B2I_E_NOMEM, "out of memory");
+	memset(p, 0, sizeof(*p));
+	p->ctx = c;
+	p->n = n;
+	p->n_deflate = (uint32_t)deflate.size();
+	p->n_stored = (uint32_t)ents.size();
+	p->n_work = (uint32_t)work.size();
+	p->n_unsup = (uint32_t)unsup.size();
+	p->need_aligned_in = !deflate.empty();
+	p->max_in_end = max_in;
+	p->max_out_end = max_out;
+
+	size_t off = 0;
+	const size_t o_descs = off;   off = align_up(off + n * sizeof(B2iDesc), 256);
+	const size_t o_order = off;   off = align_up(off + deflate.size() * 4, 256);
+	const size_t o_work = off;    off = align_up(off + work.size() * sizeof(B2iCrcWork), 256);
+	const size_t o_ents = off;    off = align_up(off + ents.size() * sizeof(B2iCrcEntry), 256);
+	const size_t o_unsup = off;   off = align_up(off + unsup.size() * 4, 256);
+	const size_t upload_bytes = off;
+	const size_t o_partial = off; off = align_up(off + work.size() * 4, 256);
+	const size_t o_counter = off; off = align_up(off + 4, 256);
+	const size_t o_results = off; off = align_up(off + n * sizeof(B2iResult), 256);
+	p->block_bytes = off;
+	p->results_off = o_results;
+
+	if (cudaMalloc(&p->d_block, off ? off : 256) != cudaSuccess ||
+	    cudaHostAlloc((void **)&p->h_block, off ? off : 256, cudaHostAllocDefault) != cudaSuccess) {
+		b2i_plan_destroy(p);
+		return fail(c, B2I_E_NOMEM, "plan allocation of %zu bytes failed", off);
+	}
+	p->d_descs = (B2iDesc *)(p->d_block + o_descs);
+	p->d_order = (uint32_t *)(p->d_block + o_order);
+	p->d_work = (B2iCrcWork *)(p->d_block + o_work);
+	p->d_ents = (B2iCrcEntry *)(p->d_block + o_ents);
+	p->d_unsup = (uint32_t *)(p->d_block + o_unsup);
+	p->d_partial = (uint32_t *)(p->d_block + o_partial);
+	p->d_counter = (unsigned int *)(p->d_block + o_counter);
+	p->d_results = (B2iResult *)(p->d_block + o_results);
+
+	if (n) memcpy(p->h_block + o_descs, descs, n * sizeof(B2iDesc));
+	if (!deflate.empty()) memcpy(p->h_block + o_order, deflate.data(), deflate.size() * 4);
+	if (!work.empty()) memcpy(p->h_block + o_work, work.data(), work.size() * sizeof(B2iCrcWork));
+	if (!ents.empty()) memcpy(p->h_block + o_ents, ents.data(), ents.size() * sizeof(B2iCrcEntry));
+	if (!unsup.empty()) memcpy(p->h_block + o_unsup, unsup.data(), unsup.size() * 4);
+	cudaError_t e = cudaMemcpyAsync(p->d_block, p->h_block, upload_bytes, cudaMemcpyHostToDevice, c->stream);
+	if (e != cudaSuccess) {
+		b2i_plan_destroy(p);
+		return fail(c, B2I_E_CUDA, "plan upload: %s", cudaGetErrorString(e));
+	}
+	*out = p;
+	return B2I_OK;
+}
+
+extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, void *d_out, size_t out_bytes)
+{
+	if (p == NULL)
+		return B2I_E_INVAL;
+	b2i_ctx *c = p->ctx;
+	if (p->n == 0)
+		return B2I_OK;
+	if (d_in == NULL || p->max_in_end > in_bytes)
+		return fail(c, B2I_E_INVAL, "input buffer too small: plan reads up to %llu, have %zu",
+		    (unsigned long long)p->max_in_end, in_bytes);
+	if (p->max_out_end > out_bytes || (p->max_out_end && d_out == NULL))
+		return fail(c, B2I_E_INVAL, "output buffer too small: plan writes up to %llu, have %zu",
+		    (unsigned long long)p->max_out_end, out_bytes);
+	if (p->need_aligned_in && ((uintptr_t)d_in & 15))
+		return fail(c, B2I_E_INVAL, "d_in must be 16-byte aligned");
+	if (p->max_out_end && ((uintptr_t)d_out & 15))
+		return fail(c, B2I_E_INVAL, "d_out must be 16-byte aligned");
+	CU(c, cudaSetDevice(c->device));
+	if (p->n_deflate) {
+		CU(c, cudaMemsetAsync(p->d_counter, 0, 4, c->stream));
+		CU(c, b2i_launch_inflate((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out, p->d_descs,
+		    p->d_results, p->d_order, p->n_deflate, p->d_counter, c->d_crc_tab, c->d_xp8,
+		    c->num_sms, c->stream));
+		c->launches++;
+	}
+	if (p->n_stored) {
+		if (p->n_work) {
+			CU(c, b2i_launch_crc_chunks((const uint8_t *)d_in, (uint8_t *)d_out, p->d_descs, p->d_work,
+			    p->n_work, p->d_partial, c->d_crc_tab, c->d_xp8, c->num_sms, c->stream));
+			c->launches++;
+		}
+		CU(c, b2i_launch_crc_combine(p->d_descs, p->d_results, p->d_ents, p->n_stored, p->d_work,
+		    p->d_partial, c->d_xp8, c->stream));
+		c->launches++;
+	}
+	if (p->n_unsup) {
+		CU(c, b2i_launch_unsupported(p->d_descs, p->d_results, p->d_unsup, p->n_unsup, c->stream));
+		c->launches++;
+	}
+	return B2I_OK;
+}
+
+extern "C" int b2i_plan_results(b2i_plan *p, b2i_stream_result *res)
+{
+	if (p == NULL || (p->n && res == NULL))
+		return B2I_E_INVAL;
+	b2i_ctx *c = p->ctx;
+	if (p->n == 0)
+		return B2I_OK;
+	CU(c, cudaMemcpyAsync(p->h_block + p->results_off, p->d_results, p->n * sizeof(B2iResult),
+	    cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	memcpy(res, p->h_block + p->results_off, p->n * sizeof(B2iResult));
+	return B2I_OK;
+}
+
+extern "C" void b2i_plan_destroy(b2i_plan *p)
+{
+	if (p == NULL)
+		return;
+	cudaSetDevice(p->ctx->device);
+	cudaStreamSynchronize(p->ctx->stream);
+	cudaFree(p->d_block);
+	cudaFreeHost(p->h_block);
+	delete p;
+}
+
+/* ---- host-buffer path --------------------------------------------------------- */
+
+static int ensure_dev(b2i_ctx *c, uint8_t **buf, size_t *cap, size_t need)
+{
+	need = align_up(need, 16) + 16;
+	if (*cap >= need)
+		return B2I_OK;
+	if (*buf) {
+		cudaStreamSynchronize(c->stream);
+		cudaFree(*buf);
+		*buf = NULL;
+		*cap = 0;
+	}
+	size_t want = std::max(need, *cap + *cap / 2);
+	if (cudaMalloc(buf, want) != cudaSuccess) {
+		if (cudaMalloc(buf, need) != cudaSuccess)
+			return fail(c, B2I_E_NOMEM, "device allocation of %zu bytes failed", need);
+		want = need;
+	}
+	*cap = want;
+	return B2I_OK;
+}
+
+extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
+    const b2i_stream_desc *descs, size_t n, void *host_out, size_t out_bytes,
+    b2i_stream_result *res)
+{
+	if (c == NULL)
+		return B2I_E_INVAL;
+	if (n == 0)
+		return B2I_OK;
+	if (host_in == NULL || descs == NULL || res == NULL)
+		return fail(c, B2I_E_INVAL, "b2i_decode_host: NULL argument");
+	CU(c, cudaSetDevice(c->device));
+	int rc;
+	if ((rc = ensure_dev(c, &c->d_in, &c->d_in_cap, in_bytes)) != B2I_OK)
+		return rc;
+	if ((rc = ensure_dev(c, &c->d_out, &c->d_out_cap, out_bytes)) != B2I_OK)
+		return rc;
+	b2i_plan *p = NULL;
+	if ((rc = b2i_plan_create(c, descs, n, &p)) != B2I_OK)
+		return rc;
+	/* only the span the streams actually touch crosses the host link */
+	uint64_t lo = ~0ull, hi = 0;
+	for (size_t i = 0; i < n; i++) {
+		if (descs[i].method != B2I_METHOD_DEFLATE && descs[i].method != B2I_METHOD_STORED)
+			continue;
+		lo = std::min<uint64_t>(lo, descs[i].in_off);
+		hi = std::max<uint64_t>(hi, descs[i].in_off + descs[i].in_len);
+	}
+	if (hi > in_bytes) {
+		b2i_plan_destroy(p);
+		return fail(c, B2I_E_INVAL, "a stream extends past the input buffer");
+	}
+	if (lo < hi) {
+		lo &= ~(uint64_t)15;
+		cudaError_t e = cudaMemcpyAsync(c->d_in + lo, (const uint8_t *)host_in + lo, hi - lo,
+		    cudaMemcpyHostToDevice, c->stream);
+		if (e != cudaSuccess) {
+			b2i_plan_destroy(p);
+			return fail(c, B2I_E_CUDA, "H2D: %s", cudaGetErrorString(e));
+		}
+	}
+	rc = b2i_plan_launch(p, c->d_in, in_bytes, c->d_out, out_bytes);
+	if (rc == B2I_OK && host_out != NULL && p->max_out_end) {
+		cudaError_t e = cudaMemcpyAsync(host_out, c->d_out, (size_t)p->max_out_end,
+		    cudaMemcpyDeviceToHost, c->stream);
+		if (e != cudaSuccess)
+			rc = fail(c, B2I_E_CUDA, "D2H: %s", cudaGetErrorString(e));
+	}
+	if (rc == B2I_OK)
+		rc = b2i_plan_results(p, res);
+	b2i_plan_destroy(p);
+	return rc;
+}
+
+/* ---- scalar CRC drop-ins ---------------------------------------------------- */
+
+static uint32_t host_mulmod(uint32_t a, uint32_t b)
+{
+	uint32_t p = 0;
+	for (int i = 0; i < 32; i++) {
+		if (a & (0x80000000u >> i))
+			p ^= b;
+		b = (b & 1) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+	}
+	return p;
+}
+
+extern "C" uint32_t b2i_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b)
+{
+	uint32_t r = 0x80000000u, sq = 0x00800000u;   /* x^0, x^8 */
+	while (len_b) {
+		if (len_b & 1)
+			r = host_mulmod(r, sq);
+		sq = host_mulmod(sq, sq);
+		len_b >>= 1;
+	}
+	return host_mulmod(r, crc_a) ^ crc_b;
+}
+
+static int crc_of_device_span(b2i_ctx *c, uint32_t crc, const void *d_buf, size_t len, uint32_t *out)
+{
+	b2i_stream_desc d;
+	b2i_stream_result r;
+	b2i_plan *p = NULL;
+	int rc;
+
+	memset(&d, 0, sizeof(d));
+	d.in_len = len;
+	d.expect_out = len;
+	d.method = B2I_METHOD_STORED;
+	d.flags = B2I_F_NO_COPY;
+	if ((rc = b2i_plan_create(c, &d, 1, &p)) != B2I_OK)
+		return rc;
+	rc = b2i_plan_launch(p, d_buf, len, NULL, 0);
+	if (rc == B2I_OK)
+		rc = b2i_plan_results(p, &r);
+	b2i_plan_destroy(p);
+	if (rc != B2I_OK)
+		return rc;
+	/* chaining: crc(c, M) = combine(c, crc(0, M), |M|)   (archive_crc32.h:43-84 contract) */
+	*out = b2i_crc32_combine(crc, r.crc, len);
+	return B2I_OK;
+}
+
+extern "C" int b2i_crc32_device(b2i_ctx *c, uint32_t crc, const void *d_buf, size_t len, uint32_t *out)
+{
+	if (c == NULL || out == NULL)
+		return B2I_E_INVAL;
+	if (d_buf == NULL) {          /* crc32(x, NULL, 0) == 0 */
+		*out = 0;
+		return B2I_OK;
+	}
+	if (len == 0) {
+		*out = crc;
+		return B2I_OK;
+	}
+	return crc_of_device_span(c, crc, d_buf, len, out);
+}
+
+extern "C" int b2i_crc32(b2i_ctx *c, uint32_t crc, const void *host_buf, size_t len, uint32_t *out)
+{
+	if (c == NULL || out == NULL)
+		return B2I_E_INVAL;
+	if (host_buf == NULL) {
+		*out = 0;
+		return B2I_OK;
+	}
+	if (len == 0) {
+		*out = crc;
+		return B2I_OK;
+	}
+	CU(c, cudaSetDevice(c->device));
+	int rc = ensure_dev(c, &c->d_in, &c->d_in_cap, len);
+	if (rc != B2I_OK)
+		return rc;
+	CU(c, cudaMemcpyAsync(c->d_in, host_buf, len, cudaMemcpyHostToDevice, c->stream));
+	return crc_of_device_span(c, crc, c->d_in, len, out);
+}
+
+extern "C" void b2i_free(void *p) { free(p); }

@@ -1,0 +1,235 @@
+/*
+ * b2i_kernels.cu — sm_100a kernels behind include/b200inflate.h.
+ *
+ *   b2i_inflate_kernel      K1: one warp per deflate stream (+ fused CRC-32)
+ *   b2i_crc_chunks_kernel   K2/K3: chunked CRC-32 (+ optional copy) of stored
+ *                           entries, one warp per 16 KiB chunk
+ *   b2i_crc_combine_kernel  K2: merges chunk partials per entry
+ *                           (crc32_combine arithmetic) and applies the
+ *                           reference's end-of-entry checks
+ *   b2i_tables_kernel       one-time: slice-by-4 tables and x^(8*2^k) powers
+ *
+ * Grid sizing: K1 keeps 28 warps (7 CTAs x 4 warps) resident per SM — the
+ * per-warp shared-memory tables (7888 B) are the limiter — and CTAs pull
+ * streams from a global counter, largest streams first, so a launch never
+ * runs more than 148 x 7 CTAs and has no tail of idle CTAs.
+ */
+#include "stream_core.cuh"
+#include "b2i_kernels.h"
+
+#define INFLATE_WARPS 4
+
+extern "C" __global__ void __launch_bounds__(INFLATE_WARPS * 32, 7)
+b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *__restrict__ out,
+    const B2iDesc *__restrict__ descs, B2iResult *__restrict__ results,
+    const uint32_t *__restrict__ order, uint32_t n, unsigned int *counter,
+    const uint32_t *__restrict__ crc_tab, const uint32_t *__restrict__ xp8)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
+	const unsigned lane = threadIdx.x & 31;
+	Ring ring;
+
+	ring_init(sm, ring);
+	for (;;) {
+		uint32_t slot = 0;
+		if (lane == 0)
+			slot = atomicAdd(counter, 1u);
+		slot = __shfl_sync(B2I_FULL, slot, 0);
+		if (slot >= n)
+			break;
+		const uint32_t idx = order[slot];
+		const B2iDesc d = descs[idx];
+		process_deflate_stream(sm, ring, in, in_total, out, d, &results[idx], crc_tab, xp8);
+		__syncwarp();
+	}
+}
+
+/* ---- stored entries ------------------------------------------------------ */
+
+extern "C" __global__ void __launch_bounds__(256)
+b2i_crc_chunks_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+    const B2iDesc *__restrict__ descs, const B2iCrcWork *__restrict__ work, uint32_t nwork,
+    uint32_t *__restrict__ partial, const uint32_t *__restrict__ crc_tab,
+    const uint32_t *__restrict__ xp8)
+{
+	__shared__ uint32_t tab[1024];
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned warps_per_block = blockDim.x >> 5;
+
+	for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+		tab[i] = crc_tab[i];
+	__syncthreads();
+	for (uint32_t w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < nwork;
+	    w += gridDim.x * warps_per_block) {
+		const B2iCrcWork k = work[w];
+		const B2iDesc d = descs[k.entry];
+		const uint8_t *src = in + d.in_off + k.rel;
+		uint32_t raw0 = 0;
+		if (!(d.flags & F_NO_CRC))
+			raw0 = crc_warp_raw0(src, k.len, tab, xp8);
+		if (lane == 0)
+			partial[w] = raw0;
+		if (!(d.flags & F_NO_COPY)) {
+			uint8_t *dst = out + d.out_off + k.rel;
+			if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+				const uint4 *s4 = (const uint4 *)src;
+				uint4 *d4 = (uint4 *)dst;
+				uint32_t n16 = k.len >> 4;
+				for (uint32_t i = lane; i < n16; i += 32)
+					d4[i] = s4[i];
+				for (uint32_t i = (n16 << 4) + lane; i < k.len; i += 32)
+					dst[i] = src[i];
+			} else {
+				for (uint32_t i = lane; i < k.len; i += 32)
+					dst[i] = src[i];
+			}
+		}
+	}
+}
+
+extern "C" __global__ void __launch_bounds__(128)
+b2i_crc_combine_kernel(const B2iDesc *__restrict__ descs, B2iResult *__restrict__ results,
+    const B2iCrcEntry *__restrict__ ents, uint32_t nents, const B2iCrcWork *__restrict__ work,
+    const uint32_t *__restrict__ partial, const uint32_t *__restrict__ xp8)
+{
+	const unsigned lane = threadIdx.x & 31;
+	const uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (e >= nents)
+		return;
+	const B2iCrcEntry ce = ents[e];
+	const B2iDesc d = descs[ce.entry];
+	uint32_t acc = 0;
+	/* raw0(entry) = XOR_j shift(raw0(chunk_j), bytes after chunk j) */
+	for (uint32_t j = lane; j < ce.nwork; j += 32) {
+		const B2iCrcWork k = work[ce.first_work + j];
+		uint64_t after = d.in_len - k.rel - k.len;
+		acc ^= crc_mulmod(partial[ce.first_work + j], crc_xpow8(after, xp8));
+	}
+	for (int o = 16; o; o >>= 1)
+		acc ^= __shfl_xor_sync(B2I_FULL, acc, o);
+	if (lane == 0) {
+		B2iResult r;
+		r.status = S_OK;
+		r.detail = 0;
+		r.flags = 0;
+		r.out_bytes = d.in_len;
+		r.in_bytes = d.in_len;
+		r.crc = 0;
+		if (!(d.flags & F_NO_COPY) && d.in_len > d.out_cap) {
+			r.status = S_OUT_OVERFLOW;     /* host sized the plan wrongly */
+		} else {
+			if (!(d.flags & F_NO_CRC)) {
+				r.crc = crc_finish(0, acc, d.in_len, xp8);
+				if (r.crc != d.expect_crc)
+					r.flags |= R_CRC_MISMATCH;
+			}
+			if ((d.in_len & 0xffffffffull) != (d.expect_out & 0xffffffffull))
+				r.flags |= R_OUT_MISMATCH;
+		}
+		results[ce.entry] = r;
+	}
+}
+
+extern "C" __global__ void
+b2i_unsupported_kernel(const B2iDesc *__restrict__ descs, B2iResult *__restrict__ results,
+    const uint32_t *__restrict__ list, uint32_t n)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	B2iResult r;
+	r.status = S_UNSUPPORTED;
+	r.crc = 0; r.out_bytes = 0; r.in_bytes = 0; r.detail = descs[list[i]].method; r.flags = 0;
+	results[list[i]] = r;
+}
+
+/* one block of 256 threads: tab[k*256+b] and xp8[k] = x^(8*2^k) */
+extern "C" __global__ void
+b2i_tables_kernel(uint32_t *crc_tab, uint32_t *xp8)
+{
+	__shared__ uint32_t t0[256];
+	const uint32_t b = threadIdx.x;
+	uint32_t c = b;
+	for (int k = 0; k < 8; k++)
+		c = (c & 1) ? (c >> 1) ^ CRC_POLY : c >> 1;
+	t0[b] = c;
+	crc_tab[b] = c;
+	__syncthreads();
+	for (int k = 1; k < 4; k++) {
+		c = t0[c & 0xff] ^ (c >> 8);
+		crc_tab[k * 256 + b] = c;
+	}
+	if (b == 0) {
+		uint32_t p = 0x00800000u;       /* x^8 */
+		for (int k = 0; k < 40; k++) {
+			xp8[k] = p;
+			p = crc_mulmod(p, p);
+		}
+	}
+}
+
+/* ---- launch wrappers (called from b2i_api.cpp; plain C++ signatures) ------ */
+
+size_t b2i_inflate_smem_bytes(void) { return sizeof(WarpSmem) * INFLATE_WARPS; }
+
+cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, cudaStream_t st)
+{
+	b2i_tables_kernel<<<1, 256, 0, st>>>(crc_tab, xp8);
+	return cudaGetLastError();
+}
+
+cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out,
+    const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
+    unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, int num_sms,
+    cudaStream_t st)
+{
+	static bool configured = false;
+	const size_t smem = b2i_inflate_smem_bytes();
+	if (!configured) {
+		cudaError_t e = cudaFuncSetAttribute(b2i_inflate_kernel,
+		    cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		if (e != cudaSuccess)
+			return e;
+		e = cudaFuncSetAttribute(b2i_inflate_kernel,
+		    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess)
+			return e;
+		configured = true;
+	}
+	uint32_t blocks = (n + INFLATE_WARPS - 1) / INFLATE_WARPS;
+	uint32_t max_blocks = (uint32_t)num_sms * 7u;
+	if (blocks > max_blocks)
+		blocks = max_blocks;
+	b2i_inflate_kernel<<<blocks, INFLATE_WARPS * 32, smem, st>>>(in, in_total, out, descs,
+	    results, order, n, counter, crc_tab, xp8);
+	return cudaGetLastError();
+}
+
+cudaError_t b2i_launch_crc_chunks(const uint8_t *in, uint8_t *out, const B2iDesc *descs,
+    const B2iCrcWork *work, uint32_t nwork, uint32_t *partial, const uint32_t *crc_tab,
+    const uint32_t *xp8, int num_sms, cudaStream_t st)
+{
+	uint32_t blocks = (nwork + 7) / 8;
+	uint32_t max_blocks = (uint32_t)num_sms * 8u;
+	if (blocks > max_blocks)
+		blocks = max_blocks;
+	b2i_crc_chunks_kernel<<<blocks, 256, 0, st>>>(in, out, descs, work, nwork, partial, crc_tab, xp8);
+	return cudaGetLastError();
+}
+
+cudaError_t b2i_launch_crc_combine(const B2iDesc *descs, B2iResult *results,
+    const B2iCrcEntry *ents, uint32_t nents, const B2iCrcWork *work, const uint32_t *partial,
+    const uint32_t *xp8, cudaStream_t st)
+{
+	b2i_crc_combine_kernel<<<(nents + 3) / 4, 128, 0, st>>>(descs, results, ents, nents, work,
+	    partial, xp8);
+	return cudaGetLastError();
+}
+
+cudaError_t b2i_launch_unsupported(const B2iDesc *descs, B2iResult *results,
+    const uint32_t *list, uint32_t n, cudaStream_t st)
+{
+	b2i_unsupported_kernel<<<(n + 127) / 128, 128, 0, st>>>(descs, results, list, n);
+	return cudaGetLastError();
+}

@@ -1,0 +1,679 @@
+/*
+ * inflate_core.cuh — one warp decodes one raw deflate stream (RFC 1951).
+ *
+ * Replaces zlib inflate() as the reference calls it per ZIP entry
+ * (archive_read_support_format_zip.c:2510-2533 init, :2643 inflate, :2647-2665
+ * result handling) and per gzip member (archive_read_support_filter_gzip.c:363,
+ * :479); accept/reject behaviour follows zlib 1.3.
+ * From-scratch design, not a port of zlib:
+ *
+ *   - the compressed bytes are staged into a per-warp shared-memory ring by
+ *     1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), two 256-byte
+ *     halves, the next half always in flight;
+ *   - a 64-bit bit buffer refilled 32 bits at a time from the ring;
+ *   - canonical-Huffman lookup tables built by the whole warp in shared
+ *     memory: lit/len 2^10 primary + secondary (<= 1334 entries), distance 2^8
+ *     primary + secondary (<= 400 entries); bounds are the exact maxima over
+ *     all complete codes (same DP as zlib's `enough`, re-derived in DESIGN.md);
+ *   - symbols are decoded warp-uniformly in batches of up to 32; lane k keeps
+ *     symbol k in registers, then the whole warp resolves the batch: a shuffle
+ *     prefix sum gives every symbol its output position, literals are stored
+ *     by their lanes in one go, matches are copied by all 32 lanes
+ *     (overlap-safe: source index taken modulo the distance);
+ *   - stored blocks are copied global->global by the warp;
+ *   - the CRC-32 of the produced bytes is computed by the same warp right
+ *     after the last block (crc32_core.cuh), while they are still in L2.
+ *
+ * All integer arithmetic; no tensor cores (not a contraction).
+ */
+#pragma once
+#include "b2i_common.cuh"
+#include "crc32_core.cuh"
+
+#define LIT_ROOT    10
+#define DIST_ROOT   8
+#define CL_ROOT     7
+#define LIT_TABLE   1336   /* >= 1334 = max over complete 288-symbol codes   */
+#define DIST_TABLE  400    /* max over complete 30/32-symbol codes, root 8   */
+#define RING_HALF   256
+#define RING_BYTES  (2 * RING_HALF)
+
+/* table entry: [4:0] bits to drop (code + extra), [7:5] kind, [11:8] code
+ * length (SUB: index bits of the sub-table), [15:12] extra-bit count,
+ * [31:16] value (literal, length base, distance base, SUB: table offset) */
+#define K_LIT   0u
+#define K_BASE  1u
+#define K_EOB   2u
+#define K_SUB   3u
+#define K_INV   4u
+#define ENTRY(kind, total, clen, eb, val) \
+	((uint32_t)(total) | ((uint32_t)(kind) << 5) | ((uint32_t)(clen) << 8) | \
+	 ((uint32_t)(eb) << 12) | ((uint32_t)(val) << 16))
+#define E_KIND(e)  (((e) >> 5) & 7u)
+#define E_TOTAL(e) ((e) & 31u)
+#define E_CLEN(e)  (((e) >> 8) & 15u)
+#define E_EB(e)    (((e) >> 12) & 15u)
+#define E_VAL(e)   ((e) >> 16)
+
+struct __align__(16) WarpSmem {
+	uint32_t lit[LIT_TABLE];
+	uint32_t dist[DIST_TABLE];
+	uint8_t  ring[RING_BYTES];
+	uint8_t  lens[320];
+	unsigned long long mbar[2];
+	uint16_t cnt[16];
+	uint16_t run[16];
+	uint8_t  cl[32];
+};
+
+/* ------------------------------------------------------------------------ */
+/* input ring                                                               */
+/* ------------------------------------------------------------------------ */
+struct Ring {
+	const uint8_t *gbase;   /* 16-byte aligned global address of segment 0 */
+	uint64_t glimit;        /* bytes available from gbase (multiple of 16) */
+	uint32_t next_issue;    /* next 256-byte segment to request            */
+	uint32_t state;         /* per half h: bit h = fills issued mod 2, bit 2+h =
+	                           latest fill has landed, bit 4+h = ever filled.
+	                           Lives as long as the warp (mbarrier phases
+	                           persist across streams). */
+};
+#define RING_PAR(h)    (1u << (h))
+#define RING_WAITED(h) (4u << (h))
+#define RING_USED(h)   (16u << (h))
+
+#ifndef B2I_HOST_EMUL
+B2I_DEV uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+B2I_DEV void mbar_init(unsigned long long *bar)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(bar)) : "memory");
+}
+B2I_DEV void ring_hw_issue(WarpSmem *sm, int h, const uint8_t *src, uint32_t bytes)
+{
+	uint32_t bar = smem_addr(&sm->mbar[h]);
+	if (bytes) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+		    :: "r"(bar), "r"(bytes) : "memory");
+		asm volatile(
+		    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		    :: "r"(smem_addr(&sm->ring[h * RING_HALF])), "l"(src), "r"(bytes), "r"(bar) : "memory");
+	} else {
+		asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+	}
+}
+B2I_DEV void ring_hw_wait(WarpSmem *sm, int h, uint32_t parity)
+{
+	uint32_t bar = smem_addr(&sm->mbar[h]);
+	uint32_t done;
+	do {
+		asm volatile(
+		    "{\n\t.reg .pred p;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+	} while (!done);
+}
+#endif
+
+/* once per warp, before the first stream */
+B2I_DEV void ring_init(WarpSmem *sm, Ring &r)
+{
+	r.state = 0;
+	r.next_issue = 0;
+#ifndef B2I_HOST_EMUL
+	if (b2i_lane() == 0) {
+		mbar_init(&sm->mbar[0]);
+		mbar_init(&sm->mbar[1]);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+#else
+	(void)sm;
+#endif
+	__syncwarp();
+}
+
+B2I_DEV void ring_issue(WarpSmem *sm, Ring &r)
+{
+	const uint32_t seg = r.next_issue++;
+	const int h = seg & 1;
+	const uint64_t off = (uint64_t)seg * RING_HALF;
+	uint32_t bytes = 0;
+	if (off < r.glimit)
+		bytes = (r.glimit - off) < RING_HALF ? (uint32_t)(r.glimit - off) : RING_HALF;
+	__syncwarp();           /* every lane is done reading the half we overwrite */
+	r.state ^= RING_PAR(h);
+	r.state = (r.state & ~RING_WAITED(h)) | RING_USED(h);
+#ifdef B2I_HOST_EMUL
+	if (b2i_lane() == 0 && bytes)
+		memcpy(&sm->ring[h * RING_HALF], r.gbase + off, bytes);
+	__syncwarp();
+#else
+	if (b2i_lane() == 0)
+		ring_hw_issue(sm, h, r.gbase + off, bytes);
+#endif
+}
+
+B2I_DEV void ring_wait(WarpSmem *sm, Ring &r, int h)
+{
+	if ((r.state & RING_WAITED(h)) || !(r.state & RING_USED(h)))
+		return;
+#ifndef B2I_HOST_EMUL
+	/* n fills issued -> the latest one completes phase (n-1) & 1 */
+	ring_hw_wait(sm, h, ((r.state >> h) & 1u) ^ 1u);
+#else
+	(void)sm;
+#endif
+	r.state |= RING_WAITED(h);
+}
+
+/* make segment `seg` readable and keep the one after it in flight */
+B2I_DEV void ring_ensure(WarpSmem *sm, Ring &r, uint32_t seg)
+{
+	if (seg >= r.next_issue) {
+		/* forward jump past everything requested: let in-flight copies land
+		 * (an mbarrier phase must complete before it is re-armed) */
+		ring_wait(sm, r, 0);
+		ring_wait(sm, r, 1);
+		r.next_issue = seg;
+	}
+	while (r.next_issue <= seg + 1)
+		ring_issue(sm, r);
+	ring_wait(sm, r, seg & 1);
+}
+
+/* ------------------------------------------------------------------------ */
+/* bit reader                                                               */
+/* ------------------------------------------------------------------------ */
+struct Bits {
+	uint64_t buf;
+	int32_t  cnt;       /* valid bits in buf */
+	uint32_t rd;        /* byte offset (from gbase) of the next word to load */
+	uint32_t rd_end;    /* lead + in_len: loads at rd >= rd_end are past the stream */
+	int32_t  over;      /* bits in buf that lie beyond the end of the stream */
+};
+
+B2I_DEV void bits_load_word(WarpSmem *sm, Ring &r, Bits &b)
+{
+	if ((b.rd & (RING_HALF - 1)) == 0)
+		ring_ensure(sm, r, b.rd / RING_HALF);
+	uint32_t w = *(const uint32_t *)&sm->ring[b.rd & (RING_BYTES - 1)];
+	b.buf |= (uint64_t)w << b.cnt;
+	b.cnt += 32;
+	b.rd += 4;
+	if (b.rd > b.rd_end)
+		b.over = (int32_t)(b.rd - b.rd_end) * 8;
+}
+
+B2I_DEV void bits_refill(WarpSmem *sm, Ring &r, Bits &b)
+{
+	if (b.cnt <= 32)
+		bits_load_word(sm, r, b);
+}
+
+B2I_DEV void bits_drop(Bits &b, uint32_t n)
+{
+	b.buf >>= n;
+	b.cnt -= (int32_t)n;
+}
+
+B2I_DEV bool bits_exhausted(const Bits &b) { return b.cnt < b.over; }
+
+/* position the reader on absolute byte `pos` (offset from gbase) */
+B2I_DEV void bits_seek(WarpSmem *sm, Ring &r, Bits &b, uint32_t pos)
+{
+	b.buf = 0;
+	b.cnt = 0;
+	b.over = 0;
+	b.rd = pos & ~3u;
+	ring_ensure(sm, r, b.rd / RING_HALF);
+	bits_load_word(sm, r, b);
+	bits_drop(b, (pos & 3u) * 8);
+	bits_refill(sm, r, b);
+}
+
+/* stream-relative position of the next unread bit */
+B2I_DEV uint64_t bits_pos(const Bits &b, uint32_t lead)
+{
+	return ((uint64_t)b.rd - lead) * 8 - (uint64_t)(int64_t)b.cnt;
+}
+
+/* ------------------------------------------------------------------------ */
+/* table construction                                                       */
+/* ------------------------------------------------------------------------ */
+#define TB_LIT   0
+#define TB_DIST  1
+#define TB_CODES 2
+
+B2I_DEV uint32_t make_entry(int type, uint32_t sym, uint32_t L)
+{
+	if (type == TB_LIT) {
+		if (sym < 256)
+			return ENTRY(K_LIT, L, L, 0, sym);
+		if (sym == 256)
+			return ENTRY(K_EOB, L, L, 0, 0);
+		if (sym > 285)
+			return ENTRY(K_INV, L, L, 0, 0);
+		uint32_t i = sym - 257, eb, base;
+		if (i < 8) { eb = 0; base = 3 + i; }
+		else if (i == 28) { eb = 0; base = 258; }
+		else { eb = (i >> 2) - 1; base = 3 + ((4 + (i & 3)) << eb); }
+		return ENTRY(K_BASE, L + eb, L, eb, base);
+	}
+	if (type == TB_DIST) {
+		if (sym > 29)
+			return ENTRY(K_INV, L, L, 0, 0);
+		uint32_t eb, base;
+		if (sym < 4) { eb = 0; base = sym + 1; }
+		else { eb = (sym >> 1) - 1; base = 1 + ((2 + (sym & 1)) << eb); }
+		return ENTRY(K_BASE, L + eb, L, eb, base);
+	}
+	return ENTRY(K_LIT, L, L, 0, sym);
+}
+
+/*
+ * Build the lookup table for `nsyms` code lengths at `lens` (shared memory).
+ * Returns 0, or 1 for an over-subscribed / disallowed incomplete set
+ * (zlib inflate_table's rule: incomplete only if the longest code is 1 bit and
+ * the table is not the code-length code).  *empty is set when no symbol has a
+ * code at all.
+ */
+B2I_DEV int build_table(WarpSmem *sm, const uint8_t *lens, int nsyms, int type,
+    uint32_t *table, int root, int cap, int *empty)
+{
+	const unsigned lane = b2i_lane();
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const int nchunk = (nsyms + 31) >> 5;
+
+	if (lane < 16)
+		sm->cnt[lane] = 0;
+	__syncwarp();
+	for (int c = 0; c < nchunk; c++) {
+		int s = c * 32 + lane;
+		unsigned L = s < nsyms ? lens[s] : 0;
+		unsigned m = __match_any_sync(B2I_FULL, L);
+		if (L && (m & lt_mask) == 0)
+			sm->cnt[L] += (uint16_t)__popc(m);
+		__syncwarp();
+	}
+	unsigned myc = (lane >= 1 && lane < 16) ? sm->cnt[lane] : 0;
+	unsigned used = __ballot_sync(B2I_FULL, myc != 0);
+	int maxlen = used ? 31 - __clz(used) : 0;
+	unsigned kraft = __reduce_add_sync(B2I_FULL, myc << (15 - (lane & 15)));
+	const int size = 1 << root;
+	*empty = (maxlen == 0);
+	if (maxlen == 0 || (kraft < 32768u && maxlen == 1 && type != TB_CODES)) {
+		/* no codes, or a single 1-bit code: unused patterns are 1-bit invalid codes */
+		for (int i = lane; i < size; i += 32)
+			table[i] = ENTRY(K_INV, 1, 1, 0, 0);
+		__syncwarp();
+		if (maxlen == 0)
+			return 0;
+	} else if (kraft != 32768u) {
+		return 1;
+	}
+	if (maxlen < root) {
+		/* nothing: replicas below still cover the whole primary table */
+	}
+	/* first canonical code of each length, kept as the running next code */
+	if (lane >= 1 && lane < 16) {
+		unsigned code = 0;
+		for (unsigned j = 1; j < lane; j++)
+			code = (code + sm->cnt[j]) << 1;
+		sm->run[lane] = (uint16_t)code;
+	}
+	__syncwarp();
+	/* secondary tables: one per root-bit prefix that holds longer codes */
+	if (maxlen > root) {
+		/* 15-bit left-aligned code space; long codes start here */
+		const unsigned x0 = (unsigned)sm->run[root + 1] << (15 - (root + 1));
+		const unsigned p0 = x0 >> (15 - root);
+		unsigned next_off = (unsigned)size;
+		for (unsigned pb = p0; pb < (unsigned)size; pb += 32) {
+			unsigned p = pb + lane;
+			unsigned bits = 0;
+			if (p < (unsigned)size) {
+				unsigned x = ((p + 1) << (15 - root)) - 1;   /* last slot of the prefix */
+				for (int L = root + 1; L <= 15; L++) {
+					unsigned end = ((unsigned)sm->run[L] + sm->cnt[L]) << (15 - L);
+					if (x < end) { bits = L - root; break; }
+				}
+			}
+			unsigned sz = bits ? (1u << bits) : 0;
+			unsigned incl = sz;
+			for (int o = 1; o < 32; o <<= 1) {
+				unsigned t = __shfl_up_sync(B2I_FULL, incl, o);
+				if ((int)lane >= o) incl += t;
+			}
+			unsigned off = next_off + incl - sz;
+			next_off += __shfl_sync(B2I_FULL, incl, 31);
+			if (bits && off + sz <= (unsigned)cap)
+				table[__brev(p) >> (32 - root)] = ENTRY(K_SUB, 0, bits, 0, off);
+		}
+		if (next_off > (unsigned)cap)
+			return 1;          /* cannot happen for a complete code (bound proven) */
+		__syncwarp();
+	}
+	/* place every symbol */
+	for (int c = 0; c < nchunk; c++) {
+		int s = c * 32 + lane;
+		unsigned L = s < nsyms ? lens[s] : 0;
+		unsigned m = __match_any_sync(B2I_FULL, L);
+		unsigned code = L ? (unsigned)sm->run[L] + __popc(m & lt_mask) : 0;
+		__syncwarp();
+		if (L && (m & lt_mask) == 0)
+			sm->run[L] += (uint16_t)__popc(m);
+		__syncwarp();
+		uint32_t e = make_entry(type, (uint32_t)s, L);
+		/* codes so short that they own >= 32 primary slots: whole warp fills */
+		unsigned wide = __ballot_sync(B2I_FULL, L != 0 && (int)L + 5 <= root);
+		while (wide) {
+			int src = __ffs(wide) - 1;
+			wide &= wide - 1;
+			unsigned wl = __shfl_sync(B2I_FULL, L, src);
+			unsigned wc = __shfl_sync(B2I_FULL, code, src);
+			uint32_t we = __shfl_sync(B2I_FULL, e, src);
+			unsigned r = __brev(wc) >> (32 - wl);
+			for (unsigned i = r + (lane << wl); i < (unsigned)size; i += 32u << wl)
+				table[i] = we;
+		}
+		if (L != 0 && (int)L + 5 > root) {
+			if ((int)L <= root) {
+				unsigned r = __brev(code) >> (32 - L);
+				for (unsigned i = r; i < (unsigned)size; i += 1u << L)
+					table[i] = e;
+			} else {
+				unsigned p = code >> (L - root);
+				uint32_t sub = table[__brev(p) >> (32 - root)];
+				unsigned sbits = E_CLEN(sub), off = E_VAL(sub);
+				unsigned low = code & ((1u << (L - root)) - 1u);
+				unsigned r = __brev(low) >> (32 - (L - root));
+				for (unsigned i = r; i < (1u << sbits); i += 1u << (L - root))
+					table[off + i] = e;
+			}
+		}
+	}
+	__syncwarp();
+	return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* one stream                                                               */
+/* ------------------------------------------------------------------------ */
+struct StreamOut {
+	int32_t  status;
+	uint32_t detail;
+	uint64_t out_bytes;
+	uint64_t in_bytes;
+};
+
+B2I_DEV uint32_t lookup(const uint32_t *table, uint64_t buf, int root)
+{
+	uint32_t e = table[(uint32_t)buf & ((1u << root) - 1u)];
+	if (E_KIND(e) == K_SUB)
+		e = table[E_VAL(e) + (((uint32_t)(buf >> root)) & ((1u << E_CLEN(e)) - 1u))];
+	return e;
+}
+
+#define FAIL(st, dt) do { res.status = (st); res.detail = (dt); goto done; } while (0)
+#define NEEDOK() do { if (bits_exhausted(b)) FAIL(S_BUF_ERROR, 0); } while (0)
+
+B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, uint64_t in_total,
+    uint64_t in_off, uint64_t in_len, uint8_t *out, uint64_t out_cap)
+{
+	const unsigned lane = b2i_lane();
+	StreamOut res;
+	Bits b;
+	uint32_t outp = 0;                      /* bytes produced (streams < 4 GiB) */
+	const uint32_t cap = (uint32_t)out_cap;
+	const uint32_t lead = (uint32_t)(in_off & 15);
+	uint32_t last;
+
+	res.status = S_OK;
+	res.detail = 0;
+	r.gbase = in_base + (in_off & ~(uint64_t)15);
+	r.glimit = ((in_total + 15) & ~(uint64_t)15) - (in_off & ~(uint64_t)15);
+	r.next_issue = 0;
+	b.rd_end = lead + (uint32_t)in_len;
+	bits_seek(sm, r, b, lead);
+
+	do {
+		uint32_t hdr;
+		bits_refill(sm, r, b);
+		hdr = (uint32_t)b.buf & 7u;
+		bits_drop(b, 3);
+		NEEDOK();
+		last = hdr & 1u;
+		hdr >>= 1;
+		if (hdr == 3)
+			FAIL(S_DATA_ERROR, D_BAD_BLOCK_TYPE);
+		if (hdr == 0) {
+			/* ---- stored block: LEN, NLEN at the next byte boundary ---- */
+			bits_drop(b, (uint32_t)b.cnt & 7u);
+			bits_refill(sm, r, b);
+			uint32_t len = (uint32_t)b.buf & 0xffffu;
+			uint32_t nlen = ((uint32_t)(b.buf >> 16)) & 0xffffu;
+			bits_drop(b, 32);
+			NEEDOK();
+			if (len != (nlen ^ 0xffffu))
+				FAIL(S_DATA_ERROR, D_BAD_STORED_LEN);
+			uint32_t pos = b.rd - ((uint32_t)b.cnt >> 3);     /* byte offset from gbase */
+			uint32_t avail = b.rd_end > pos ? b.rd_end - pos : 0;
+			uint32_t ncopy = len < avail ? len : avail;
+			if (ncopy > cap - outp) {
+				FAIL(S_OUT_OVERFLOW, 0);
+			}
+			const uint8_t *src = r.gbase + pos;
+			uint8_t *dst = out + outp;
+			for (uint32_t i = lane; i < ncopy; i += 32)
+				dst[i] = src[i];
+			__syncwarp();
+			outp += ncopy;
+			bits_seek(sm, r, b, pos + ncopy);
+			if (ncopy < len) {
+				b.over = 1 << 20;  /* input ran out inside the block */
+				FAIL(S_BUF_ERROR, 0);
+			}
+			continue;
+		}
+		if (hdr == 1) {
+			/* ---- fixed Huffman: lengths from RFC 1951 3.2.6 ---- */
+			for (int i = lane; i < 288; i += 32)
+				sm->lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+			sm->lens[288 + lane] = 5;
+			__syncwarp();
+			int e0;
+			build_table(sm, sm->lens, 288, TB_LIT, sm->lit, LIT_ROOT, LIT_TABLE, &e0);
+			build_table(sm, sm->lens + 288, 32, TB_DIST, sm->dist, DIST_ROOT, DIST_TABLE, &e0);
+		} else {
+			/* ---- dynamic Huffman header ---- */
+			bits_refill(sm, r, b);
+			uint32_t nlen = ((uint32_t)b.buf & 31u) + 257;
+			uint32_t ndist = (((uint32_t)b.buf >> 5) & 31u) + 1;
+			uint32_t ncode = (((uint32_t)b.buf >> 10) & 15u) + 4;
+			bits_drop(b, 14);
+			NEEDOK();
+			if (nlen > 286 || ndist > 30)
+				FAIL(S_DATA_ERROR, D_TOO_MANY_SYMS);
+			sm->cl[lane] = 0;
+			__syncwarp();
+			for (uint32_t i = 0; i < ncode; i++) {
+				/* order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15, packed 5 bits each */
+				const uint64_t ord_lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 |
+				    7ull << 25 | 9ull << 30 | 6ull << 35 | 10ull << 40 | 5ull << 45 | 11ull << 50 | 4ull << 55;
+				const uint64_t ord_hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 |
+				    1ull << 25 | 15ull << 30;
+				uint32_t sym = i < 12 ? (uint32_t)(ord_lo >> (5 * i)) & 31u
+				                      : (uint32_t)(ord_hi >> (5 * (i - 12))) & 31u;
+				bits_refill(sm, r, b);
+				if (lane == 0)
+					sm->cl[sym] = (uint8_t)((uint32_t)b.buf & 7u);
+				bits_drop(b, 3);
+				NEEDOK();
+			}
+			__syncwarp();
+			int cl_empty;
+			if (build_table(sm, sm->cl, 19, TB_CODES, sm->dist, CL_ROOT, DIST_TABLE, &cl_empty))
+				FAIL(S_DATA_ERROR, D_BAD_CODELEN_SET);
+			uint32_t have = 0, prev = 0;
+			const uint32_t want = nlen + ndist;
+			while (have < want) {
+				bits_refill(sm, r, b);
+				uint32_t e = sm->dist[(uint32_t)b.buf & ((1u << CL_ROOT) - 1u)];
+				uint32_t sym = E_VAL(e);
+				if (E_KIND(e) == K_INV)
+					sym = 0;    /* zlib quirk: empty code-length code reads as length 0, 1 bit */
+				bits_drop(b, E_TOTAL(e));
+				NEEDOK();
+				if (sym < 16) {
+					if (lane == 0)
+						sm->lens[have] = (uint8_t)sym;
+					prev = sym;
+					have++;
+					continue;
+				}
+				uint32_t copy, fill;
+				if (sym == 16) {
+					copy = 3 + ((uint32_t)b.buf & 3u);
+					bits_drop(b, 2);
+					NEEDOK();
+					if (have == 0)
+						FAIL(S_DATA_ERROR, D_BAD_BITLEN_REPEAT);
+					fill = prev;
+				} else if (sym == 17) {
+					copy = 3 + ((uint32_t)b.buf & 7u);
+					bits_drop(b, 3);
+					NEEDOK();
+					fill = 0;
+				} else {
+					copy = 11 + ((uint32_t)b.buf & 127u);
+					bits_drop(b, 7);
+					NEEDOK();
+					fill = 0;
+				}
+				if (have + copy > want)
+					FAIL(S_DATA_ERROR, D_BAD_BITLEN_REPEAT);
+				for (uint32_t i = lane; i < copy; i += 32)
+					sm->lens[have + i] = (uint8_t)fill;
+				prev = fill;
+				have += copy;
+			}
+			__syncwarp();
+			if (sm->lens[256] == 0)
+				FAIL(S_DATA_ERROR, D_NO_EOB);
+			int e0;
+			if (build_table(sm, sm->lens, (int)nlen, TB_LIT, sm->lit, LIT_ROOT, LIT_TABLE, &e0))
+				FAIL(S_DATA_ERROR, D_BAD_LITLEN_SET);
+			if (build_table(sm, sm->lens + nlen, (int)ndist, TB_DIST, sm->dist, DIST_ROOT,
+			    DIST_TABLE, &e0))
+				FAIL(S_DATA_ERROR, D_BAD_DIST_SET);
+		}
+
+		/* ---- symbols: batches of up to 32, lane k keeps symbol k ---- */
+		for (;;) {
+			uint32_t my_len = 0, my_val = 0;
+			uint32_t n = 0;
+			int32_t stop = 0;        /* 0 go on, 1 EOB, <0 status, detail in stop_detail */
+			uint32_t stop_detail = 0;
+
+			while (n < 32) {
+				bits_refill(sm, r, b);
+				uint32_t e = lookup(sm->lit, b.buf, LIT_ROOT);
+				uint32_t kind = E_KIND(e);
+				if (kind == K_LIT) {
+					bits_drop(b, E_TOTAL(e));
+					if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
+					if (lane == n) { my_len = 1; my_val = E_VAL(e); }
+					n++;
+					continue;
+				}
+				if (kind == K_BASE) {
+					uint32_t len = E_VAL(e) + (((uint32_t)(b.buf >> E_CLEN(e))) & ((1u << E_EB(e)) - 1u));
+					bits_drop(b, E_TOTAL(e));
+					if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
+					bits_refill(sm, r, b);
+					uint32_t d = lookup(sm->dist, b.buf, DIST_ROOT);
+					if (E_KIND(d) != K_BASE) {
+						/* zlib judges the code with only its own bits */
+						bits_drop(b, E_TOTAL(d));
+						if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
+						stop = S_DATA_ERROR; stop_detail = D_BAD_DIST_CODE;
+						break;
+					}
+					uint32_t dist = E_VAL(d) + (((uint32_t)(b.buf >> E_CLEN(d))) & ((1u << E_EB(d)) - 1u));
+					bits_drop(b, E_TOTAL(d));
+					if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
+					if (lane == n) { my_len = len; my_val = dist; }
+					n++;
+					continue;
+				}
+				bits_drop(b, E_TOTAL(e));
+				if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
+				if (kind == K_EOB) { stop = 1; break; }
+				stop = S_DATA_ERROR; stop_detail = D_BAD_LITLEN_CODE;
+				break;
+			}
+
+			/* ---- resolve the batch ---- */
+			uint32_t len = lane < n ? my_len : 0;
+			uint32_t incl = len;
+			for (int o = 1; o < 32; o <<= 1) {
+				uint32_t t = __shfl_up_sync(B2I_FULL, incl, o);
+				if ((int)lane >= o) incl += t;
+			}
+			uint32_t rel = incl - len;                /* offset inside the batch */
+			bool is_match = len >= 3;
+			/* first symbol that cannot be written: bad distance or no room */
+			bool far = is_match && my_val > outp + rel;
+			bool full = len != 0 && (rel + len > cap - outp);
+			unsigned badmask = __ballot_sync(B2I_FULL, far || full);
+			if (badmask) {
+				int first = __ffs(badmask) - 1;
+				bool first_far = __shfl_sync(B2I_FULL, (int)far, first) != 0;
+				n = (uint32_t)first;
+				if (lane >= n) { len = 0; is_match = false; }
+				stop = first_far ? S_DATA_ERROR : S_OUT_OVERFLOW;
+				stop_detail = first_far ? D_DIST_TOO_FAR : 0;
+			}
+			uint32_t total = __shfl_sync(B2I_FULL, incl, n ? n - 1 : 0);
+			if (n == 0) total = 0;
+			uint8_t *dst = out + outp;
+			if (len == 1)
+				dst[rel] = (uint8_t)my_val;
+			unsigned mm = __ballot_sync(B2I_FULL, is_match);
+			__syncwarp();
+			while (mm) {
+				int src_lane = __ffs(mm) - 1;
+				mm &= mm - 1;
+				uint32_t mrel = __shfl_sync(B2I_FULL, rel, src_lane);
+				uint32_t mlen = __shfl_sync(B2I_FULL, len, src_lane);
+				uint32_t mdist = __shfl_sync(B2I_FULL, my_val, src_lane);
+				uint8_t *d = dst + mrel;
+				if (mdist >= mlen) {
+					for (uint32_t j = lane; j < mlen; j += 32)
+						d[j] = d[(int64_t)j - (int64_t)mdist];
+				} else {
+					for (uint32_t j = lane; j < mlen; j += 32)
+						d[j] = d[(int64_t)(j % mdist) - (int64_t)mdist];
+				}
+				__syncwarp();
+			}
+			outp += total;
+			if (stop == 1)
+				break;
+			if (stop < 0)
+				FAIL(stop, stop_detail);
+		}
+	} while (!last);
+done:
+	__syncwarp();
+	/* no bulk copy may still be in flight into this warp's ring when the
+	 * shared memory is handed to the next stream or the CTA exits */
+	ring_wait(sm, r, 0);
+	ring_wait(sm, r, 1);
+	res.out_bytes = outp;
+	res.in_bytes = (bits_pos(b, lead) + 7) >> 3;
+	return res;
+}
+#undef FAIL
+#undef NEEDOK

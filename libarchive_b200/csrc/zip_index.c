@@ -1,0 +1,386 @@
+/*
+ * zip_index.c — host side of the seekable ZIP reader, flattened: locate the
+ * end-of-central-directory record, walk the central directory once into flat
+ * arrays, sort by local-header offset, and resolve every entry's data offset
+ * and definitive CRC/sizes from its local header.  The result is what the
+ * batch plan is built from (one descriptor per entry).
+ *
+ * Written from the ZIP APPNOTE; the acceptance rules and field precedence
+ * follow the reference reader so that both see the same entries:
+ *   EOCD search in the last 16 KiB, last match wins, i > 0 only
+ *       archive_read_support_format_zip.c:3720-3773 (seekable_bid)
+ *   EOCD sanity checks and cd offset                      :3635-3669 (read_eocd)
+ *   ZIP64 locator exactly 20 bytes before the EOCD        :3675-3718
+ *   forward scan for the first PK\1\2 / PK\5\6 / PK\6\6 => `correction`
+ *                                                         :3887-3924
+ *   46-byte central records until PK\5\6 / PK\6\6         :3936-3986
+ *   ZIP64 extra 0x0001: usize, csize, offset in that order, each only when
+ *   the 32-bit field is 0xffffffff                        :526-577
+ *   iteration in ascending local-header offset, duplicates of one offset
+ *   dropped (red-black tree insert)                       :3778-3789, 4031, 4298-4303
+ *   local header: flags/method/crc/sizes/name/extra, reconciliation with the
+ *   central values (local wins when non-zero, WARN on mismatch),
+ *   data start = offset + 30 + name + extra               :936-972, 1106-1150
+ *
+ * No allocation per entry, no tree: two passes over flat arrays.
+ */
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/b200inflate.h"
+
+#define ZIP_ENCRYPTED          (1 << 0)
+#define ZIP_LENGTH_AT_END      (1 << 3)
+#define ZIP_STRONG_ENCRYPTED   (1 << 6)
+
+#define IFMT   0170000u
+#define IFDIR  0040000u
+#define IFREG  0100000u
+#define IFIFO  0010000u
+
+static uint16_t le16(const uint8_t *p) { return (uint16_t)(p[0] | p[1] << 8); }
+static uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+static uint64_t le64(const uint8_t *p) { return (uint64_t)le32(p) | (uint64_t)le32(p + 4) << 32; }
+
+static int
+err(char errbuf[128], const char *msg)
+{
+	if (errbuf)
+		snprintf(errbuf, 128, "%s", msg);
+	return B2I_E_FORMAT;
+}
+
+/* MS-DOS date/time -> time_t, as libarchive/archive_time.c dos_to_unix does
+ * (local time zone interpretation through mktime) */
+#include <time.h>
+static int64_t
+dos_time(uint32_t d)
+{
+	struct tm ts;
+	uint16_t msTime = (uint16_t)(0xffff & d), msDate = (uint16_t)(d >> 16);
+
+	memset(&ts, 0, sizeof(ts));
+	ts.tm_year = ((msDate >> 9) & 0x7f) + 80;
+	ts.tm_mon = ((msDate >> 5) & 0x0f) - 1;
+	ts.tm_mday = msDate & 0x1f;
+	ts.tm_hour = (msTime >> 11) & 0x1f;
+	ts.tm_min = (msTime >> 5) & 0x3f;
+	ts.tm_sec = (msTime << 1) & 0x3e;
+	ts.tm_isdst = -1;
+	return (int64_t)mktime(&ts);
+}
+
+struct cdrec {
+	uint64_t lho, csize, usize;
+	uint32_t crc, idx, mode;
+	int64_t  mtime;
+	uint16_t flags;
+	uint8_t  method;
+};
+
+/* ZIP64 extended information, with the reference's order and conditions.
+ * Returns 0, or -1 on the "Malformed 64-bit ..." / overflow conditions. */
+static int
+apply_extra(const uint8_t *p, size_t n, uint64_t *usize, uint64_t *csize, uint64_t *lho,
+    int64_t *mtime, const char **why)
+{
+	size_t off = 0;
+
+	if (n == 0)
+		return 0;
+	if (n < 4) {
+		for (size_t i = 0; i < n; i++)
+			if (p[i] != 0) { *why = "Too-small extra data"; return -1; }
+		return 0;
+	}
+	while (off <= n - 4) {
+		uint16_t id = le16(p + off), sz = le16(p + off + 2);
+		size_t o;
+		off += 4;
+		if (off + sz > n) { *why = "Extra data overflow"; return -1; }
+		o = off;
+		if (id == 0x0001) {
+			unsigned left = sz;
+			if (*usize == 0xffffffffull) {
+				uint64_t t;
+				if (left < 8 || (t = le64(p + o)) > INT64_MAX) { *why = "Malformed 64-bit uncompressed size"; return -1; }
+				*usize = t; o += 8; left -= 8;
+			}
+			if (*csize == 0xffffffffull) {
+				uint64_t t;
+				if (left < 8 || (t = le64(p + o)) > INT64_MAX) { *why = "Malformed 64-bit compressed size"; return -1; }
+				*csize = t; o += 8; left -= 8;
+			}
+			if (lho && *lho == 0xffffffffull) {
+				uint64_t t;
+				if (left < 8 || (t = le64(p + o)) > INT64_MAX) { *why = "Malformed 64-bit local header offset"; return -1; }
+				*lho = t; o += 8; left -= 8;
+			}
+		} else if (id == 0x5455 && sz >= 1) {
+			/* extended timestamp: mtime first when flag bit 0 is set */
+			if ((p[o] & 1) && sz >= 5)
+				*mtime = (int32_t)le32(p + o + 1);
+		}
+		off += sz;
+	}
+	return 0;
+}
+
+static int
+cmp_rec(const void *a, const void *b)
+{
+	const struct cdrec *x = a, *y = b;
+	if (x->lho != y->lho)
+		return x->lho < y->lho ? -1 : 1;
+	return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+
+int
+b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char errbuf[128])
+{
+	const uint8_t *base = archive;
+	int64_t cd_offset = -1, cd_adjusted = -1;
+	size_t tail, tail_start;
+	long i;
+	int found = 0;
+
+	if (out == NULL || (archive == NULL && size))
+		return B2I_E_INVAL;
+	memset(out, 0, sizeof(*out));
+	if (errbuf)
+		errbuf[0] = 0;
+	if (size == 0)
+		return err(errbuf, "empty file");
+
+	/* --- end of central directory: last PK\5\6 in the final 16 KiB, i > 0 --- */
+	tail = size < 16384 ? size : 16384;
+	tail_start = size - tail;
+	for (i = (long)tail - 22; i > 0; i--) {
+		const uint8_t *p = base + tail_start + i;
+		if (memcmp(p, "PK\005\006", 4) != 0)
+			continue;
+		{
+			int64_t pos = (int64_t)(tail_start + i);
+			uint16_t disk = le16(p + 4);
+			uint32_t cd_size = le32(p + 12), cd_off = le32(p + 16);
+			if (disk == 0 && le16(p + 6) == 0 && le16(p + 10) == le16(p + 8) &&
+			    (int64_t)cd_off + cd_size <= pos) {
+				cd_offset = cd_off;
+				cd_adjusted = pos - cd_size;
+				found = 1;
+			}
+			if (i >= 20 && memcmp(p - 20, "PK\006\007", 4) == 0) {
+				const uint8_t *l = p - 20;
+				if (le32(l + 4) == 0 && le32(l + 16) == 1) {
+					uint64_t e64 = le64(l + 8);
+					if (e64 <= size && size - e64 >= 56) {
+						const uint8_t *q = base + e64;
+						uint64_t e64size = le64(q + 4) + 12;
+						if (e64size >= 56 && e64size <= 16384 && size - e64 >= e64size &&
+						    le32(q + 16) == 0 && le32(q + 20) == 0 &&
+						    le64(q + 24) == le64(q + 32)) {
+							cd_offset = (int64_t)le64(q + 48);
+							cd_adjusted = cd_offset;
+							found = 1;
+						}
+					}
+				}
+			}
+		}
+		break;      /* only the last EOCD signature is examined */
+	}
+	if (!found)
+		return err(errbuf, "no end-of-central-directory record");
+	if (cd_adjusted < 0 || (uint64_t)cd_adjusted > size)
+		return err(errbuf, "central directory offset out of range");
+
+	/* --- real start of the directory => correction for prepended data --- */
+	size_t pos = (size_t)cd_adjusted;
+	for (found = 0; pos + 4 < size; pos++) {
+		const uint8_t *p = base + pos;
+		if (p[0] == 'P' && p[1] == 'K' &&
+		    ((p[2] == 1 && p[3] == 2) || (p[2] == 5 && p[3] == 6) || (p[2] == 6 && p[3] == 6))) {
+			found = 1;
+			break;
+		}
+	}
+	if (!found || size - pos < 20)
+		return err(errbuf, "central directory not found");
+	out->correction = (int64_t)pos - cd_offset;
+
+	/* --- pass 1: count records --- */
+	size_t n = 0, q = pos;
+	for (;;) {
+		if (size - q < 4)
+			return err(errbuf, "truncated central directory");
+		if (memcmp(base + q, "PK\006\006", 4) == 0 || memcmp(base + q, "PK\005\006", 4) == 0)
+			break;
+		if (memcmp(base + q, "PK\001\002", 4) != 0)
+			return err(errbuf, "Invalid central directory signature");
+		if (size - q < 46)
+			return err(errbuf, "truncated central directory");
+		size_t var = (size_t)le16(base + q + 28) + le16(base + q + 30);
+		if (size - q - 46 < var)
+			return err(errbuf, "Truncated ZIP file header");
+		q += 46 + var + le16(base + q + 32);
+		if (q > size)
+			q = size;       /* a long comment may run off the end; the next read fails */
+		n++;
+	}
+
+	struct cdrec *recs = malloc((n ? n : 1) * sizeof(*recs));
+	if (recs == NULL)
+		return B2I_E_NOMEM;
+
+	/* --- pass 2: decode records --- */
+	q = pos;
+	for (size_t k = 0; k < n; k++) {
+		const uint8_t *p = base + q;
+		struct cdrec *r = &recs[k];
+		uint32_t ext = le32(p + 38);
+		size_t nl = le16(p + 28), xl = le16(p + 30), cl = le16(p + 32);
+		const char *why = NULL;
+		uint64_t lho32 = le32(p + 42);
+
+		r->idx = (uint32_t)k;
+		r->flags = le16(p + 8);
+		if (r->flags & (ZIP_ENCRYPTED | ZIP_STRONG_ENCRYPTED))
+			out->has_encrypted_entries = 1;
+		r->method = (uint8_t)le16(p + 10);
+		r->mtime = dos_time(le32(p + 12));
+		r->crc = le32(p + 16);
+		r->csize = le32(p + 20);
+		r->usize = le32(p + 24);
+		/* the reference adds the correction BEFORE testing for 0xffffffff, so a
+		 * ZIP64 offset is only honoured when the correction is zero (zip.c:3985, :559) */
+		r->lho = lho32 + (uint64_t)out->correction;
+		if (p[5] == 3)
+			r->mode = ext >> 16;
+		else if (p[5] == 0) {
+			r->mode = (ext & 0x10) ? (IFDIR | 0775) : (IFREG | 0664);
+			if (ext & 0x01)
+				r->mode &= 0555 | IFMT;
+		} else
+			r->mode = 0;
+		if (apply_extra(p + 46 + nl, xl, &r->usize, &r->csize, &r->lho, &r->mtime, &why) != 0) {
+			free(recs);
+			return err(errbuf, why);
+		}
+		q += 46 + nl + xl + cl;
+	}
+
+	/* --- ascending local-header offset; first record of an offset wins --- */
+	qsort(recs, n, sizeof(*recs), cmp_rec);
+	size_t m = 0;
+	for (size_t k = 0; k < n; k++)
+		if (m == 0 || recs[k].lho != recs[m - 1].lho)
+			recs[m++] = recs[k];
+
+	b2i_zip_entry *ents = calloc(m ? m : 1, sizeof(*ents));
+	size_t names_cap = 0;
+	for (size_t k = 0; k < m; k++)
+		if (recs[k].lho <= size && size - recs[k].lho >= 30)
+			names_cap += le16(base + recs[k].lho + 26);
+	char *names = malloc(names_cap ? names_cap : 1);
+	if (ents == NULL || names == NULL) {
+		free(recs); free(ents); free(names);
+		return B2I_E_NOMEM;
+	}
+
+	/* --- pass 3: local headers --- */
+	size_t names_len = 0;
+	for (size_t k = 0; k < m; k++) {
+		const struct cdrec *r = &recs[k];
+		b2i_zip_entry *e = &ents[k];
+
+		e->local_header_offset = r->lho;
+		e->compressed_size = r->csize;
+		e->uncompressed_size = r->usize;
+		e->crc32 = r->crc;
+		e->zip_flags = r->flags;
+		e->method = r->method;
+		e->mode = r->mode;
+		e->mtime = r->mtime;
+		if (r->lho > size || size - r->lho < 30) {
+			e->warn |= B2I_ZW_TRUNCATED;
+			continue;
+		}
+		const uint8_t *p = base + r->lho;
+		if (memcmp(p, "PK\003\004", 4) != 0) {
+			e->warn |= B2I_ZW_BAD_LOCAL_HEADER;
+			continue;
+		}
+		size_t nl = le16(p + 26), xl = le16(p + 28);
+		if (size - r->lho - 30 < nl + xl) {
+			e->warn |= B2I_ZW_TRUNCATED;
+			continue;
+		}
+		uint64_t l_usize = le32(p + 22), l_csize = le32(p + 18);
+		uint32_t l_crc = le32(p + 14);
+		int64_t l_mtime = dos_time(le32(p + 10));
+		const char *why = NULL;
+
+		e->version = p[4];
+		e->system = p[5];
+		e->zip_flags = le16(p + 6);
+		e->method = (uint8_t)le16(p + 8);
+		e->name_offset = (uint32_t)names_len;
+		e->name_len = (uint16_t)nl;
+		memcpy(names + names_len, p + 30, nl);
+		names_len += nl;
+		if (apply_extra(p + 30 + nl, xl, &l_usize, &l_csize, NULL, &l_mtime, &why) != 0) {
+			e->warn |= B2I_ZW_BAD_LOCAL_HEADER;
+			continue;
+		}
+		e->mtime = l_mtime;
+		e->data_offset = r->lho + 30 + nl + xl;
+		/* central values are definitive; local ones win when present (zip.c:1106-1150) */
+		e->zip_flags &= (uint16_t)~ZIP_LENGTH_AT_END;
+		if (l_crc != 0) {
+			if (l_crc != r->crc)
+				e->warn |= B2I_ZW_CRC_INCONSISTENT;
+			e->crc32 = l_crc;
+		}
+		if (l_csize != 0 && l_csize != 0xffffffffull) {
+			if (l_csize != r->csize)
+				e->warn |= B2I_ZW_CSIZE_INCONSISTENT;
+			e->compressed_size = l_csize;
+		}
+		if (l_usize != 0 && l_usize != 0xffffffffull) {
+			if (l_usize != r->usize)
+				e->warn |= B2I_ZW_USIZE_INCONSISTENT;
+			e->uncompressed_size = l_usize;
+		}
+		if (e->data_offset > size || size - e->data_offset < e->compressed_size)
+			e->warn |= B2I_ZW_TRUNCATED;
+		/* file type fix-ups (zip.c:1029-1062) */
+		if ((e->mode & IFMT) == IFIFO)
+			e->mode = (e->mode & ~IFMT) | IFREG;
+		if (e->mode == 0)
+			e->mode |= 0664;
+		if ((e->mode & IFMT) != IFDIR) {
+			if (nl > 0 && p[30 + nl - 1] == '/')
+				e->mode = (e->mode & ~IFMT) | IFDIR | 0111;
+			else if ((e->mode & IFMT) == 0)
+				e->mode |= IFREG;
+		}
+	}
+	free(recs);
+	out->n = m;
+	out->entries = ents;
+	out->names = names;
+	out->names_len = names_len;
+	return B2I_OK;
+}
+
+void
+b2i_zip_index_free(b2i_zip_index *ix)
+{
+	if (ix == NULL)
+		return;
+	free(ix->entries);
+	free(ix->names);
+	memset(ix, 0, sizeof(*ix));
+}

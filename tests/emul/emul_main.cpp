@@ -1,0 +1,93 @@
+/*
+ * emul_main.cpp — TEST INFRASTRUCTURE ONLY: runs the device per-stream code of
+ * libarchive_b200/csrc on the host under warp_emul.h (32 pthreads = 1 warp).
+ */
+#define B2I_HOST_EMUL 1
+#include "../../libarchive_b200/csrc/stream_core.cuh"
+#include <stdlib.h>
+#include <vector>
+
+thread_local unsigned tl_lane;
+thread_local EmulWarp *tl_warp;
+
+static uint32_t g_crc_tab[1024];
+static uint32_t g_xp8[40];
+static int g_tab_ready;
+
+static void make_tables()
+{
+	for (uint32_t b = 0; b < 256; b++) {
+		uint32_t c = b;
+		for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ CRC_POLY : c >> 1;
+		g_crc_tab[b] = c;
+	}
+	for (int k = 1; k < 4; k++)
+		for (uint32_t b = 0; b < 256; b++) {
+			uint32_t c = g_crc_tab[(k - 1) * 256 + b];
+			g_crc_tab[k * 256 + b] = g_crc_tab[c & 0xff] ^ (c >> 8);
+		}
+	uint32_t p = 0x00800000u; /* x^8 */
+	for (int k = 0; k < 40; k++) { g_xp8[k] = p; p = crc_mulmod(p, p); }
+	g_tab_ready = 1;
+}
+
+struct Job {
+	EmulWarp warp;
+	WarpSmem sm;
+	const uint8_t *in; uint64_t in_total; uint8_t *out;
+	B2iDesc d; B2iResult res;
+	int mode; /* 0 inflate+crc, 1 crc of in[in_off, +in_len) */
+	uint32_t crc_out;
+};
+struct LaneArg { Job *job; unsigned lane; };
+
+static void *lane_main(void *p)
+{
+	LaneArg *a = (LaneArg *)p;
+	Job *j = a->job;
+	tl_lane = a->lane;
+	tl_warp = &j->warp;
+	if (j->mode == 0) {
+		Ring ring;
+		ring_init(&j->sm, ring);
+		process_deflate_stream(&j->sm, ring, j->in, j->in_total, j->out, j->d, &j->res, g_crc_tab, g_xp8);
+	} else {
+		crc_load_tables(j->sm.lit, g_crc_tab);
+		uint32_t raw0 = crc_warp_raw0(j->in + j->d.in_off, j->d.in_len, j->sm.lit, g_xp8);
+		uint32_t c = crc_finish(j->d.expect_crc, raw0, j->d.in_len, g_xp8);
+		if (tl_lane == 0) j->crc_out = c;
+	}
+	return NULL;
+}
+
+static void run(Job *j)
+{
+	pthread_t th[32];
+	LaneArg args[32];
+	pthread_barrier_init(&j->warp.bar, NULL, 32);
+	for (unsigned i = 0; i < 32; i++) { args[i].job = j; args[i].lane = i; pthread_create(&th[i], NULL, lane_main, &args[i]); }
+	for (unsigned i = 0; i < 32; i++) pthread_join(th[i], NULL);
+	pthread_barrier_destroy(&j->warp.bar);
+}
+
+extern "C" int emul_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out, const B2iDesc *d, B2iResult *res)
+{
+	if (!g_tab_ready) make_tables();
+	Job *j = new Job();
+	j->in = in; j->in_total = in_total; j->out = out; j->d = *d; j->mode = 0;
+	run(j);
+	*res = j->res;
+	delete j;
+	return 0;
+}
+
+extern "C" uint32_t emul_crc32(uint32_t crc, const uint8_t *buf, uint64_t off, uint64_t len)
+{
+	if (!g_tab_ready) make_tables();
+	Job *j = new Job();
+	j->in = buf; j->d.in_off = off; j->d.in_len = len; j->d.expect_crc = crc; j->mode = 1;
+	run(j);
+	uint32_t c = j->crc_out;
+	delete j;
+	return c;
+}

