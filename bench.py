@@ -254,7 +254,10 @@ def main():
     archive, kind = build_workload(args.workload, rank, args.scale)
     descs, out_bytes, usize, csize = plan_for(archive, kind)
     n = len(descs)
-    stream = torch.cuda.current_stream()
+    # a dedicated stream shared by torch (events) and the library (kernels, copies);
+    # the legacy default stream has handle 0, which the C ABI reads as "make your own"
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = capi.Context(local_rank, stream.cuda_stream)
     L = capi.lib()
 

@@ -119,13 +119,45 @@ def test_single_bit_corruptions(ctx):
 
 
 def test_output_capacity_overflow(ctx):
+    """A stream that wants more room than its descriptor reserves stops with
+    B2I_S_OUT_OVERFLOW and never writes past its capacity (device buffer is
+    pre-filled with a sentinel through the explicit plan API)."""
     txt = synth.synth_text(50000, 12)
     s = synth.deflate_raw(txt, 6)
-    descs, res, gout, ores, oout = run_streams(ctx, [s, s, s], caps=[1000, 49999, 50000])
+    caps = [1000, 49999, 50000]
+    L = capi.lib()
+    items, out = [], 0
+    for k, cap in enumerate(caps):
+        d = StreamDesc()
+        d.in_off, d.in_len, d.method = 0, len(s), 8
+        d.out_off, d.out_cap = out, cap
+        out = (out + cap + 15 + 64) & ~15
+        items.append(d)
+    descs = capi.make_descs(items)
+    d_in = L.b2i_device_alloc(ctx.h, len(s))
+    d_out = L.b2i_device_alloc(ctx.h, out)
+    sentinel = b"\xEE" * out
+    ctx._check(L.b2i_memcpy_h2d(ctx.h, d_in, s, len(s)))
+    ctx._check(L.b2i_memcpy_h2d(ctx.h, d_out, sentinel, out))
+    plan = C.c_void_p()
+    ctx._check(L.b2i_plan_create(ctx.h, descs, 3, C.byref(plan)))
+    ctx._check(L.b2i_plan_launch(plan, d_in, len(s), d_out, out))
+    res = (capi.StreamResult * 3)()
+    ctx._check(L.b2i_plan_results(plan, res))
+    host = C.create_string_buffer(out)
+    ctx._check(L.b2i_memcpy_d2h(ctx.h, host, d_out, out))
+    ctx.sync()
+    L.b2i_plan_destroy(plan)
+    L.b2i_device_free(ctx.h, d_in)
+    L.b2i_device_free(ctx.h, d_out)
     assert [r.status for r in res] == [capi.S_OUT_OVERFLOW, capi.S_OUT_OVERFLOW, 0]
-    assert gout[descs[2].out_off:descs[2].out_off + 50000] == txt
-    # nothing is written past a stream's capacity
-    assert gout[descs[0].out_off + 1000:descs[0].out_off + 1008] == bytes(8)
+    g = host.raw
+    for k, cap in enumerate(caps):
+        o = descs[k].out_off
+        assert g[o:o + res[k].out_bytes] == txt[:res[k].out_bytes]
+        assert res[k].out_bytes <= cap
+        assert g[o + cap:o + cap + 64] == b"\xEE" * 64, "wrote past capacity of stream %d" % k
+    assert g[descs[2].out_off:descs[2].out_off + 50000] == txt
 
 
 def test_many_streams_one_pass(ctx):
