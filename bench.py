@@ -360,7 +360,7 @@ def main():
                      "algorithmic_bytes_per_launch": usize + csize, "launch_ms": kern_ms,
                      "out_frac_of_hbm": (usize / (kern_ms * 1e-3) / 1e9) / peak},
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": csize + n * 48,
-                "d2h_bytes_per_step": out_bytes + n * 40, "ms_per_step": e2e_ms / K},
+                "d2h_bytes_per_step": out_bytes + n * 32, "ms_per_step": e2e_ms / K},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

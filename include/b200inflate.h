@@ -8,17 +8,17 @@
  *
  *   reference call site                                    replaced by
  *   ----------------------------------------------------   --------------------------
- *   inflateInit2/inflateReset/inflate/inflateEnd           b2i_plan_* / b2i_submit
+ *   inflateInit2/inflateReset/inflate/inflateEnd           b2i_plan_* / b2i_decode_host
  *     archive_read_support_format_zip.c:2510-2533, 2643    (one descriptor per entry,
  *     archive_read_support_filter_gzip.c:357-363, 479      one device pass per batch)
  *   crc32() through zip->crc32func (real_crc32)            fused in the inflate pass;
- *     archive_read_support_format_zip.c:405-409, 3154-3157 b2i_crc32() for the scalar
+ *     archive_read_support_format_zip.c:405-409, 3154-3157 b2i_crc32 for the scalar
  *     archive_crc32.h:43-84 (semantics)                    drop-in
  *   zip_read_data_none                                     method 0 descriptors
  *     archive_read_support_format_zip.c:1592-1706          (CRC in place, optional copy)
- *   slurp_central_directory / zip_read_local_file_header   b2i_zip_index()
+ *   slurp_central_directory / zip_read_local_file_header   b2i_zip_index_build
  *     archive_read_support_format_zip.c:3867-4092, 905-972 (host, flat arrays)
- *   peek_at_header / consume_header / consume_trailer      b2i_gzip_scan()
+ *   peek_at_header / consume_header / consume_trailer      b2i_gzip_scan_bgzf
  *     archive_read_support_filter_gzip.c:128-239, 340-429  (host; BGZF BSIZE chain)
  *
  * Error model: infrastructure failures (bad arguments, CUDA errors, OOM) are

@@ -509,6 +509,9 @@ def deflate_zoo():
     ll5[0] = ll5[1] = ll5[2] = 1
     ll5[256] = 1
     add("dyn_oversubscribed_litlen", dynamic_header(BitWriter(), ll5, [1]).put(0, 16))
+    # over-subscribed / incomplete distance trees
+    add("dyn_oversubscribed_dist", dynamic_header(BitWriter(), ll, [1, 1, 1]).put(0, 16))
+    add("dyn_incomplete_dist", dynamic_header(BitWriter(), ll, [2, 2, 2]).put(0, 16))
     # missing end-of-block code
     ll6 = [0] * 257
     ll6[0] = ll6[1] = 1

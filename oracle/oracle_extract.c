@@ -143,7 +143,8 @@ cmd_list(const void *buf, size_t len, int raw, const char *opt, const char *dump
 			if (nblk < 8)
 				first_blocks[nblk] = bsz;
 			nblk++;
-			crc = crc32(crc, blk, (uInt)bsz);
+			if (bsz > 0)
+				crc = crc32(crc, blk, (uInt)bsz);
 			nbytes += bsz;
 			if (df)
 				fwrite(blk, 1, bsz, df);

@@ -1,0 +1,89 @@
+"""The warp-level device code (table construction, batch resolution, ring logic,
+CRC merge tree) compiled for the host under tests/emul (32 pthreads = 1 warp) and
+checked against the oracle - the not-gpu suite's coverage of the kernel logic.
+The TMA/mbarrier PTX itself is only exercised by the -m gpu tests."""
+import ctypes as C
+import hashlib
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import test_gpu_reader as gr
+from emul_ctx import EmulContext, emu
+from libarchive_b200 import capi, reader, synth
+from libarchive_b200.capi import StreamDesc, StreamResult
+
+
+def emul_inflate(s, cap, lead=0):
+    buf = bytes(lead) + s
+    inb = C.create_string_buffer(buf + bytes(48), len(buf) + 48)
+    out = C.create_string_buffer(cap + 64)
+    d = StreamDesc()
+    d.in_off, d.in_len, d.out_cap, d.method = lead, len(s), cap, 8
+    r = StreamResult()
+    emu().emul_inflate(inb, len(buf), out, C.byref(d), C.byref(r))
+    return r, out.raw[:r.out_bytes]
+
+
+def check(name, s, cap=1 << 18, leads=(0, 5)):
+    o, od = ob.inflate(s, cap)
+    for lead in leads:
+        r, ed = emul_inflate(s, cap, lead)
+        assert r.status == o.status, (name, lead, r.status, r.detail, o.status, o.detail)
+        assert ed == od, (name, lead)
+        if o.status == 0:
+            assert r.in_bytes == o.in_bytes and r.crc == (zlib.crc32(od) & 0xFFFFFFFF), name
+        if o.status == -3:
+            assert r.detail == o.detail, name
+
+
+def test_zoo():
+    for name, s in synth.deflate_zoo():
+        check(name, s)
+
+
+def test_random_dynamic_blocks():
+    for seed in range(12):
+        check("rand%d" % seed, synth.random_dynamic_stream(100 + seed, 1200), leads=(seed % 16,))
+
+
+def test_text_fixed_stored_and_errors():
+    txt = synth.synth_text(70000, 2)
+    full = synth.deflate_raw(txt[:65536], 6)
+    check("text", full, leads=(3,))
+    check("fixed", synth.deflate_raw(txt[:9000], 6, zlib.Z_FIXED), leads=(1,))
+    check("stored", synth.deflate_raw(synth.synth_random(40000), 6), leads=(15,))
+    check("rle", synth.deflate_raw(bytes(70000), 6), leads=(0,))
+    check("cut", full[:4000], leads=(2,))
+    check("junk", synth.deflate_raw(txt[:800], 6) + b"JUNKJUNK", leads=(0,))
+    r, out = emul_inflate(synth.deflate_raw(txt[:5000], 6), 1000)
+    assert r.status == capi.S_OUT_OVERFLOW and r.out_bytes <= 1000 and out == txt[:r.out_bytes]
+
+
+def test_crc_lengths_alignments():
+    rng = np.random.default_rng(3)
+    for n in [0, 1, 15, 16, 17, 31, 32, 100, 511, 512, 513, 1000, 4096, 65536, 65537, 100001]:
+        for off in (0, 3):
+            data = rng.integers(0, 256, n + off + 64, dtype=np.uint8).tobytes()
+            buf = C.create_string_buffer(data, len(data))
+            assert emu().emul_crc32(0, buf, off, n) == (zlib.crc32(data[off:off + n]) & 0xFFFFFFFF), (n, off)
+            assert emu().emul_crc32(0xABCD, buf, off, n) == (zlib.crc32(data[off:off + n], 0xABCD) & 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("name", gr.ZIP_NAMES)
+def test_reader_on_reference_zip_fixtures(name):
+    gr.test_reference_zip_fixture(EmulContext(), name)
+
+
+@pytest.mark.parametrize("name", gr.GZ_NAMES)
+def test_reader_on_reference_gzip_fixtures(name):
+    gr.test_reference_gzip_fixture(EmulContext(), name)
+
+
+def test_reader_error_messages():
+    gr.test_entry_errors_match_reference_messages(EmulContext())
+    gr.test_ignorecrc32_option(EmulContext())
