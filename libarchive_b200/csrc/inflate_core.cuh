@@ -8,18 +8,22 @@
  * From-scratch design, not a port of zlib:
  *
  *   - the compressed bytes are staged into a per-warp shared-memory ring by
- *     1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), two 256-byte
+ *     1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), two 128-byte
  *     halves, the next half always in flight;
- *   - a 64-bit bit buffer refilled 32 bits at a time from the ring;
+ *   - a 64-bit bit buffer refilled 32 bits at a time from the ring, kept
+ *     pre-shifted by 2 so that (low word & 0xFFC) is the byte offset of the
+ *     primary table entry;
  *   - canonical-Huffman lookup tables built by the whole warp in shared
  *     memory: lit/len 2^10 primary + secondary (<= 1334 entries), distance 2^8
  *     primary + secondary (<= 400 entries); bounds are the exact maxima over
- *     all complete codes (same DP as zlib's `enough`, re-derived in DESIGN.md);
+ *     all complete codes;
  *   - symbols are decoded warp-uniformly in batches of up to 32; lane k keeps
- *     symbol k in registers, then the whole warp resolves the batch: a shuffle
- *     prefix sum gives every symbol its output position, literals are stored
- *     by their lanes in one go, matches are copied by all 32 lanes
- *     (overlap-safe: source index taken modulo the distance);
+ *     symbol k in a register.  The batch is then resolved by all lanes, one
+ *     output byte per lane: a shuffle binary search over the prefix sums finds
+ *     the owning symbol, literals and bytes fetched from already flushed output
+ *     (four loads in flight per lane) go into a shared-memory staging buffer,
+ *     the few bytes whose source lies in the same batch are patched from the
+ *     staging buffer, and the batch leaves as aligned 16-byte stores;
  *   - stored blocks are copied global->global by the warp;
  *   - the CRC-32 of the produced bytes is computed by the same warp right
  *     after the last block (crc32_core.cuh), while they are still in L2.
@@ -35,36 +39,77 @@
 #define CL_ROOT     7
 #define LIT_TABLE   1336   /* >= 1334 = max over complete 288-symbol codes   */
 #define DIST_TABLE  400    /* max over complete 30/32-symbol codes, root 8   */
-#define RING_HALF   256
+#define RING_HALF   128
 #define RING_BYTES  (2 * RING_HALF)
 
-/* table entry: [4:0] bits to drop (code + extra), [7:5] kind, [11:8] code
- * length (SUB: index bits of the sub-table), [15:12] extra-bit count,
- * [31:16] value (literal, length base, distance base, SUB: table offset) */
-#define K_LIT   0u
-#define K_BASE  1u
-#define K_EOB   2u
-#define K_SUB   3u
-#define K_INV   4u
-#define ENTRY(kind, total, clen, eb, val) \
-	((uint32_t)(total) | ((uint32_t)(kind) << 5) | ((uint32_t)(clen) << 8) | \
-	 ((uint32_t)(eb) << 12) | ((uint32_t)(val) << 16))
-#define E_KIND(e)  (((e) >> 5) & 7u)
-#define E_TOTAL(e) ((e) & 31u)
-#define E_CLEN(e)  (((e) >> 8) & 15u)
-#define E_EB(e)    (((e) >> 12) & 15u)
-#define E_VAL(e)   ((e) >> 16)
+/*
+ * Table entries (32 bit).  Common: [4:0] bits to drop (code + extra),
+ * bit 5 LIT, bit 6 SLOW.
+ *   literal  (lit/len table) : LIT,  [24:8] = 0x10000 | byte   (= the batch record)
+ *   length   (lit/len table) : [12:8] code length + 2, [23:16] extra-bit mask,
+ *                              [31:24] base - 3
+ *   distance (dist table)    : [12:8] code length + 2, [16:13] extra-bit count,
+ *                              [31:17] base
+ *   code-length symbol       : LIT,  [31:8] symbol
+ *   SLOW kinds [13:12]       : 0 sub-table ([11:8] index bits, [31:16] offset),
+ *                              1 end of block, 2 invalid code
+ * "code length + 2" because the bit buffer is kept shifted left by 2.
+ */
+#define E_LIT        0x20u
+#define E_SLOW       0x40u
+#define E_TOTAL(e)   ((e) & 31u)
+#define SK_SUB       0u
+#define SK_EOB       1u
+#define SK_INV       2u
+#define E_SLOWKIND(e) (((e) >> 12) & 3u)
+#define E_SUBBITS(e) (((e) >> 8) & 15u)
+#define E_SUBOFF(e)  ((e) >> 16)
+#define ENTRY_INV(total)      ((uint32_t)(total) | E_SLOW | (SK_INV << 12))
+#define ENTRY_EOB(total)      ((uint32_t)(total) | E_SLOW | (SK_EOB << 12))
+#define ENTRY_SUB(bits, off)  (E_SLOW | (SK_SUB << 12) | ((uint32_t)(bits) << 8) | ((uint32_t)(off) << 16))
 
-struct __align__(16) WarpSmem {
-	uint32_t lit[LIT_TABLE];
-	uint32_t dist[DIST_TABLE];
-	uint8_t  ring[RING_BYTES];
+/* Output staging: a batch of symbols is assembled here and leaves for global
+ * memory as aligned 16-byte stores.  It shares its space with the block-header
+ * scratch (code lengths, counters), which is only live while a header is parsed. */
+#define STAGE_BYTES 832
+#define BATCH_SOFT  559   /* keep decoding while the batch holds <= this many
+                             bytes: 15 (carry) + 559 + 258 (one more match) = 832 */
+struct HeaderScratch {
 	uint8_t  lens[320];
-	unsigned long long mbar[2];
 	uint16_t cnt[16];
 	uint16_t run[16];
 	uint8_t  cl[32];
 };
+struct __align__(16) WarpSmem {
+	uint32_t lit[LIT_TABLE];
+	uint32_t dist[DIST_TABLE];
+	uint8_t  ring[RING_BYTES];
+	union {
+		HeaderScratch h;
+		uint8_t stage[STAGE_BYTES];
+	} u;
+	unsigned long long mbar[2];
+};
+
+/* ------------------------------------------------------------------------ */
+/* small PTX helpers                                                        */
+/* ------------------------------------------------------------------------ */
+#ifndef B2I_HOST_EMUL
+/* low 32 bits of (hi:lo) >> (n mod 32) */
+B2I_DEV uint32_t shf_r_wrap(uint32_t lo, uint32_t hi, uint32_t n)
+{
+	uint32_t r;
+	asm("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(n));
+	return r;
+}
+B2I_DEV uint32_t byte2(uint32_t e) { return __byte_perm(e, 0, 0x4442); }
+#else
+B2I_DEV uint32_t shf_r_wrap(uint32_t lo, uint32_t hi, uint32_t n)
+{
+	return (uint32_t)((((uint64_t)hi << 32) | lo) >> (n & 31));
+}
+B2I_DEV uint32_t byte2(uint32_t e) { return (e >> 16) & 0xffu; }
+#endif
 
 /* ------------------------------------------------------------------------ */
 /* input ring                                                               */
@@ -72,7 +117,7 @@ struct __align__(16) WarpSmem {
 struct Ring {
 	const uint8_t *gbase;   /* 16-byte aligned global address of segment 0 */
 	uint64_t glimit;        /* bytes available from gbase (multiple of 16) */
-	uint32_t next_issue;    /* next 256-byte segment to request            */
+	uint32_t next_issue;    /* next segment to request                     */
 	uint32_t state;         /* per half h: bit h = fills issued mod 2, bit 2+h =
 	                           latest fill has landed, bit 4+h = ever filled.
 	                           Lives as long as the warp (mbarrier phases
@@ -168,7 +213,7 @@ B2I_DEV void ring_wait(WarpSmem *sm, Ring &r, int h)
 }
 
 /* make segment `seg` readable and keep the one after it in flight */
-B2I_DEV void ring_ensure(WarpSmem *sm, Ring &r, uint32_t seg)
+B2I_DEV_NOINLINE void ring_ensure(WarpSmem *sm, Ring &r, uint32_t seg)
 {
 	if (seg >= r.next_issue) {
 		/* forward jump past everything requested: let in-flight copies land
@@ -183,46 +228,56 @@ B2I_DEV void ring_ensure(WarpSmem *sm, Ring &r, uint32_t seg)
 }
 
 /* ------------------------------------------------------------------------ */
-/* bit reader                                                               */
+/* bit reader: (hi:lo) holds the unread bits shifted left by 2               */
 /* ------------------------------------------------------------------------ */
 struct Bits {
-	uint64_t buf;
-	int32_t  cnt;       /* valid bits in buf */
+	uint32_t lo, hi;
+	int32_t  cnt;       /* valid bits */
 	uint32_t rd;        /* byte offset (from gbase) of the next word to load */
 	uint32_t rd_end;    /* lead + in_len: loads at rd >= rd_end are past the stream */
-	int32_t  over;      /* bits in buf that lie beyond the end of the stream */
+	int32_t  over;      /* buffered bits that lie beyond the end of the stream */
 };
 
+/* requires cnt <= 30 */
 B2I_DEV void bits_load_word(WarpSmem *sm, Ring &r, Bits &b)
 {
 	if ((b.rd & (RING_HALF - 1)) == 0)
 		ring_ensure(sm, r, b.rd / RING_HALF);
 	uint32_t w = *(const uint32_t *)&sm->ring[b.rd & (RING_BYTES - 1)];
-	b.buf |= (uint64_t)w << b.cnt;
+	uint64_t W = (((uint64_t)b.hi << 32) | b.lo) | ((uint64_t)w << (b.cnt + 2));
+	b.lo = (uint32_t)W;
+	b.hi = (uint32_t)(W >> 32);
 	b.cnt += 32;
 	b.rd += 4;
 	if (b.rd > b.rd_end)
 		b.over = (int32_t)(b.rd - b.rd_end) * 8;
 }
 
+/* afterwards cnt >= 31: enough for any lit/len code + extra (20) or distance
+ * code + extra (28) */
 B2I_DEV void bits_refill(WarpSmem *sm, Ring &r, Bits &b)
 {
-	if (b.cnt <= 32)
+	if (b.cnt <= 30)
 		bits_load_word(sm, r, b);
 }
 
+/* n <= 31 (the shifter takes n mod 32); the two low bits may hold junk afterwards */
 B2I_DEV void bits_drop(Bits &b, uint32_t n)
 {
-	b.buf >>= n;
-	b.cnt -= (int32_t)n;
+	b.lo = shf_r_wrap(b.lo, b.hi, n);
+	b.hi = shf_r_wrap(b.hi, 0, n);
+	b.cnt -= (int32_t)(n & 31u);
 }
+
+/* the next (up to 30) unread bits, right aligned */
+B2I_DEV uint32_t bits_peek(const Bits &b) { return shf_r_wrap(b.lo, b.hi, 2); }
 
 B2I_DEV bool bits_exhausted(const Bits &b) { return b.cnt < b.over; }
 
 /* position the reader on absolute byte `pos` (offset from gbase) */
 B2I_DEV void bits_seek(WarpSmem *sm, Ring &r, Bits &b, uint32_t pos)
 {
-	b.buf = 0;
+	b.lo = b.hi = 0;
 	b.cnt = 0;
 	b.over = 0;
 	b.rd = pos & ~3u;
@@ -249,84 +304,79 @@ B2I_DEV uint32_t make_entry(int type, uint32_t sym, uint32_t L)
 {
 	if (type == TB_LIT) {
 		if (sym < 256)
-			return ENTRY(K_LIT, L, L, 0, sym);
+			return L | E_LIT | ((0x10000u | sym) << 8);
 		if (sym == 256)
-			return ENTRY(K_EOB, L, L, 0, 0);
+			return ENTRY_EOB(L);
 		if (sym > 285)
-			return ENTRY(K_INV, L, L, 0, 0);
+			return ENTRY_INV(L);
 		uint32_t i = sym - 257, eb, base;
 		if (i < 8) { eb = 0; base = 3 + i; }
 		else if (i == 28) { eb = 0; base = 258; }
 		else { eb = (i >> 2) - 1; base = 3 + ((4 + (i & 3)) << eb); }
-		return ENTRY(K_BASE, L + eb, L, eb, base);
+		return (L + eb) | ((L + 2) << 8) | (((1u << eb) - 1u) << 16) | ((base - 3) << 24);
 	}
 	if (type == TB_DIST) {
 		if (sym > 29)
-			return ENTRY(K_INV, L, L, 0, 0);
+			return ENTRY_INV(L);
 		uint32_t eb, base;
 		if (sym < 4) { eb = 0; base = sym + 1; }
 		else { eb = (sym >> 1) - 1; base = 1 + ((2 + (sym & 1)) << eb); }
-		return ENTRY(K_BASE, L + eb, L, eb, base);
+		return (L + eb) | ((L + 2) << 8) | (eb << 13) | (base << 17);
 	}
-	return ENTRY(K_LIT, L, L, 0, sym);
+	return L | E_LIT | (sym << 8);
 }
 
 /*
  * Build the lookup table for `nsyms` code lengths at `lens` (shared memory).
  * Returns 0, or 1 for an over-subscribed / disallowed incomplete set
  * (zlib inflate_table's rule: incomplete only if the longest code is 1 bit and
- * the table is not the code-length code).  *empty is set when no symbol has a
- * code at all.
+ * the table is not the code-length code).
  */
-B2I_DEV int build_table(WarpSmem *sm, const uint8_t *lens, int nsyms, int type,
-    uint32_t *table, int root, int cap, int *empty)
+B2I_DEV_NOINLINE int build_table(WarpSmem *sm, const uint8_t *lens, int nsyms, int type,
+    uint32_t *table, int root, int cap)
 {
 	const unsigned lane = b2i_lane();
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const int nchunk = (nsyms + 31) >> 5;
 
 	if (lane < 16)
-		sm->cnt[lane] = 0;
+		sm->u.h.cnt[lane] = 0;
 	__syncwarp();
 	for (int c = 0; c < nchunk; c++) {
 		int s = c * 32 + lane;
 		unsigned L = s < nsyms ? lens[s] : 0;
 		unsigned m = __match_any_sync(B2I_FULL, L);
 		if (L && (m & lt_mask) == 0)
-			sm->cnt[L] += (uint16_t)__popc(m);
+			sm->u.h.cnt[L] += (uint16_t)__popc(m);
 		__syncwarp();
 	}
-	unsigned myc = (lane >= 1 && lane < 16) ? sm->cnt[lane] : 0;
+	unsigned myc = (lane >= 1 && lane < 16) ? sm->u.h.cnt[lane] : 0;
 	unsigned used = __ballot_sync(B2I_FULL, myc != 0);
 	int maxlen = used ? 31 - __clz(used) : 0;
 	unsigned kraft = __reduce_add_sync(B2I_FULL, myc << (15 - (lane & 15)));
 	const int size = 1 << root;
-	*empty = (maxlen == 0);
 	if (maxlen == 0 || (kraft < 32768u && maxlen == 1 && type != TB_CODES)) {
 		/* no codes, or a single 1-bit code: unused patterns are 1-bit invalid codes */
 		for (int i = lane; i < size; i += 32)
-			table[i] = ENTRY(K_INV, 1, 1, 0, 0);
+			table[i] = ENTRY_INV(1);
 		__syncwarp();
 		if (maxlen == 0)
 			return 0;
 	} else if (kraft != 32768u) {
 		return 1;
 	}
-	if (maxlen < root) {
-		/* nothing: replicas below still cover the whole primary table */
-	}
 	/* first canonical code of each length, kept as the running next code */
 	if (lane >= 1 && lane < 16) {
 		unsigned code = 0;
 		for (unsigned j = 1; j < lane; j++)
-			code = (code + sm->cnt[j]) << 1;
-		sm->run[lane] = (uint16_t)code;
+			code = (code + sm->u.h.cnt[j]) << 1;
+		sm->u.h.run[lane] = (uint16_t)code;
 	}
 	__syncwarp();
 	/* secondary tables: one per root-bit prefix that holds longer codes */
 	if (maxlen > root) {
 		/* 15-bit left-aligned code space; long codes start here */
-		const unsigned x0 = (unsigned)sm->run[root + 1] << (15 - (root + 1));
+		const unsigned x0 = (unsigned)sm->u.h.run[root + 1] << (15 - (root + 1));
 		const unsigned p0 = x0 >> (15 - root);
 		unsigned next_off = (unsigned)size;
 		for (unsigned pb = p0; pb < (unsigned)size; pb += 32) {
@@ -335,7 +385,7 @@ B2I_DEV int build_table(WarpSmem *sm, const uint8_t *lens, int nsyms, int type,
 			if (p < (unsigned)size) {
 				unsigned x = ((p + 1) << (15 - root)) - 1;   /* last slot of the prefix */
 				for (int L = root + 1; L <= 15; L++) {
-					unsigned end = ((unsigned)sm->run[L] + sm->cnt[L]) << (15 - L);
+					unsigned end = ((unsigned)sm->u.h.run[L] + sm->u.h.cnt[L]) << (15 - L);
 					if (x < end) { bits = L - root; break; }
 				}
 			}
@@ -348,7 +398,7 @@ B2I_DEV int build_table(WarpSmem *sm, const uint8_t *lens, int nsyms, int type,
 			unsigned off = next_off + incl - sz;
 			next_off += __shfl_sync(B2I_FULL, incl, 31);
 			if (bits && off + sz <= (unsigned)cap)
-				table[__brev(p) >> (32 - root)] = ENTRY(K_SUB, 0, bits, 0, off);
+				table[__brev(p) >> (32 - root)] = ENTRY_SUB(bits, off);
 		}
 		if (next_off > (unsigned)cap)
 			return 1;          /* cannot happen for a complete code (bound proven) */
@@ -359,10 +409,10 @@ B2I_DEV int build_table(WarpSmem *sm, const uint8_t *lens, int nsyms, int type,
 		int s = c * 32 + lane;
 		unsigned L = s < nsyms ? lens[s] : 0;
 		unsigned m = __match_any_sync(B2I_FULL, L);
-		unsigned code = L ? (unsigned)sm->run[L] + __popc(m & lt_mask) : 0;
+		unsigned code = L ? (unsigned)sm->u.h.run[L] + __popc(m & lt_mask) : 0;
 		__syncwarp();
 		if (L && (m & lt_mask) == 0)
-			sm->run[L] += (uint16_t)__popc(m);
+			sm->u.h.run[L] += (uint16_t)__popc(m);
 		__syncwarp();
 		uint32_t e = make_entry(type, (uint32_t)s, L);
 		/* codes so short that they own >= 32 primary slots: whole warp fills */
@@ -385,7 +435,7 @@ B2I_DEV int build_table(WarpSmem *sm, const uint8_t *lens, int nsyms, int type,
 			} else {
 				unsigned p = code >> (L - root);
 				uint32_t sub = table[__brev(p) >> (32 - root)];
-				unsigned sbits = E_CLEN(sub), off = E_VAL(sub);
+				unsigned sbits = E_SUBBITS(sub), off = E_SUBOFF(sub);
 				unsigned low = code & ((1u << (L - root)) - 1u);
 				unsigned r = __brev(low) >> (32 - (L - root));
 				for (unsigned i = r; i < (1u << sbits); i += 1u << (L - root))
@@ -398,6 +448,85 @@ B2I_DEV int build_table(WarpSmem *sm, const uint8_t *lens, int nsyms, int type,
 }
 
 /* ------------------------------------------------------------------------ */
+/* symbol decoding: one batch                                               */
+/* ------------------------------------------------------------------------ */
+
+/* second-level lookup for a SUB entry */
+B2I_DEV uint32_t lookup_sub(const uint32_t *table, const Bits &b, uint32_t e, int root)
+{
+	uint32_t idx = shf_r_wrap(b.lo, b.hi, root + 2) & ((1u << E_SUBBITS(e)) - 1u);
+	return table[E_SUBOFF(e) + idx];
+}
+
+/*
+ * Decode symbols until 32 are held, the batch is full, the block ends or an
+ * error shows.  Lane k keeps symbol k as (length << 16 | literal-or-distance).
+ * CHECK = false is used while the stream has so much input left that no symbol
+ * of this batch can run past its end (no per-symbol exhaustion test).
+ * Returns 0 go on, 1 end of block, < 0 a B2I status (detail in *detail).
+ */
+template <bool CHECK>
+B2I_DEV int decode_batch(WarpSmem *sm, Ring &r, Bits &b, uint32_t &my, uint32_t &n_out,
+    uint32_t &detail)
+{
+	const unsigned lane = b2i_lane();
+	const char *litp = (const char *)sm->lit;
+	const char *distp = (const char *)sm->dist;
+	uint32_t n = 0, cum = 0;
+	int stop = 0;
+
+	my = 0;
+	while (n < 32 && cum <= BATCH_SOFT) {
+		bits_refill(sm, r, b);
+		uint32_t e = *(const uint32_t *)(litp + (b.lo & ((1u << (LIT_ROOT + 2)) - 4u)));
+		if (e & E_SLOW) {
+			if (E_SLOWKIND(e) == SK_SUB)
+				e = lookup_sub(sm->lit, b, e, LIT_ROOT);
+			if (e & E_SLOW) {
+				bits_drop(b, e);
+				if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
+				if (E_SLOWKIND(e) == SK_EOB) { stop = 1; break; }
+				stop = S_DATA_ERROR; detail = D_BAD_LITLEN_CODE;
+				break;
+			}
+		}
+		if (e & E_LIT) {
+			bits_drop(b, e);
+			if (CHECK && bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
+			if (lane == n) my = e >> 8;
+			n++;
+			cum++;
+			continue;
+		}
+		/* length: base - 3 in the top byte, extra bits above the code */
+		uint32_t len = (e >> 24) + (shf_r_wrap(b.lo, b.hi, e >> 8) & byte2(e)) + 3u;
+		bits_drop(b, e);
+		if (CHECK && bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
+		bits_refill(sm, r, b);
+		uint32_t d = *(const uint32_t *)(distp + (b.lo & ((1u << (DIST_ROOT + 2)) - 4u)));
+		if (d & E_SLOW) {
+			if (E_SLOWKIND(d) == SK_SUB)
+				d = lookup_sub(sm->dist, b, d, DIST_ROOT);
+			if (d & E_SLOW) {
+				/* zlib judges the code with only its own bits */
+				bits_drop(b, d);
+				if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
+				stop = S_DATA_ERROR; detail = D_BAD_DIST_CODE;
+				break;
+			}
+		}
+		uint32_t dist = (d >> 17) + (shf_r_wrap(b.lo, b.hi, d >> 8) & ((1u << ((d >> 13) & 15u)) - 1u));
+		bits_drop(b, d);
+		if (CHECK && bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
+		if (lane == n) my = (len << 16) | dist;
+		n++;
+		cum += len;
+	}
+	n_out = n;
+	return stop;
+}
+
+/* ------------------------------------------------------------------------ */
 /* one stream                                                               */
 /* ------------------------------------------------------------------------ */
 struct StreamOut {
@@ -406,14 +535,6 @@ struct StreamOut {
 	uint64_t out_bytes;
 	uint64_t in_bytes;
 };
-
-B2I_DEV uint32_t lookup(const uint32_t *table, uint64_t buf, int root)
-{
-	uint32_t e = table[(uint32_t)buf & ((1u << root) - 1u)];
-	if (E_KIND(e) == K_SUB)
-		e = table[E_VAL(e) + (((uint32_t)(buf >> root)) & ((1u << E_CLEN(e)) - 1u))];
-	return e;
-}
 
 #define FAIL(st, dt) do { res.status = (st); res.detail = (dt); goto done; } while (0)
 #define NEEDOK() do { if (bits_exhausted(b)) FAIL(S_BUF_ERROR, 0); } while (0)
@@ -425,6 +546,10 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, 
 	StreamOut res;
 	Bits b;
 	uint32_t outp = 0;                      /* bytes produced (streams < 4 GiB) */
+	/* The last (outp & 15) bytes produced are not in global memory yet: lane i
+	 * (i < outp & 15) keeps byte (outp & ~15) + i in `carry`, so that every
+	 * store of decoded data is a full, aligned 16-byte unit. */
+	uint32_t carry = 0;
 	const uint32_t cap = (uint32_t)out_cap;
 	const uint32_t lead = (uint32_t)(in_off & 15);
 	uint32_t last;
@@ -440,7 +565,7 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, 
 	do {
 		uint32_t hdr;
 		bits_refill(sm, r, b);
-		hdr = (uint32_t)b.buf & 7u;
+		hdr = bits_peek(b) & 7u;
 		bits_drop(b, 3);
 		NEEDOK();
 		last = hdr & 1u;
@@ -451,24 +576,29 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, 
 			/* ---- stored block: LEN, NLEN at the next byte boundary ---- */
 			bits_drop(b, (uint32_t)b.cnt & 7u);
 			bits_refill(sm, r, b);
-			uint32_t len = (uint32_t)b.buf & 0xffffu;
-			uint32_t nlen = ((uint32_t)(b.buf >> 16)) & 0xffffu;
-			bits_drop(b, 32);
+			uint32_t len = bits_peek(b) & 0xffffu;
+			bits_drop(b, 16);
+			bits_refill(sm, r, b);
+			uint32_t nlen = bits_peek(b) & 0xffffu;
+			bits_drop(b, 16);
 			NEEDOK();
 			if (len != (nlen ^ 0xffffu))
 				FAIL(S_DATA_ERROR, D_BAD_STORED_LEN);
 			uint32_t pos = b.rd - ((uint32_t)b.cnt >> 3);     /* byte offset from gbase */
 			uint32_t avail = b.rd_end > pos ? b.rd_end - pos : 0;
 			uint32_t ncopy = len < avail ? len : avail;
-			if (ncopy > cap - outp) {
+			if (ncopy > cap - outp)
 				FAIL(S_OUT_OVERFLOW, 0);
-			}
 			const uint8_t *src = r.gbase + pos;
 			uint8_t *dst = out + outp;
+			if (lane < (outp & 15u))
+				out[(outp & ~15u) + lane] = (uint8_t)carry;
 			for (uint32_t i = lane; i < ncopy; i += 32)
 				dst[i] = src[i];
 			__syncwarp();
 			outp += ncopy;
+			if (lane < (outp & 15u))
+				carry = out[(outp & ~15u) + lane];
 			bits_seek(sm, r, b, pos + ncopy);
 			if (ncopy < len) {
 				b.over = 1 << 20;  /* input ran out inside the block */
@@ -479,23 +609,23 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, 
 		if (hdr == 1) {
 			/* ---- fixed Huffman: lengths from RFC 1951 3.2.6 ---- */
 			for (int i = lane; i < 288; i += 32)
-				sm->lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
-			sm->lens[288 + lane] = 5;
+				sm->u.h.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+			sm->u.h.lens[288 + lane] = 5;
 			__syncwarp();
-			int e0;
-			build_table(sm, sm->lens, 288, TB_LIT, sm->lit, LIT_ROOT, LIT_TABLE, &e0);
-			build_table(sm, sm->lens + 288, 32, TB_DIST, sm->dist, DIST_ROOT, DIST_TABLE, &e0);
+			build_table(sm, sm->u.h.lens, 288, TB_LIT, sm->lit, LIT_ROOT, LIT_TABLE);
+			build_table(sm, sm->u.h.lens + 288, 32, TB_DIST, sm->dist, DIST_ROOT, DIST_TABLE);
 		} else {
 			/* ---- dynamic Huffman header ---- */
 			bits_refill(sm, r, b);
-			uint32_t nlen = ((uint32_t)b.buf & 31u) + 257;
-			uint32_t ndist = (((uint32_t)b.buf >> 5) & 31u) + 1;
-			uint32_t ncode = (((uint32_t)b.buf >> 10) & 15u) + 4;
+			uint32_t h14 = bits_peek(b);
+			uint32_t nlen = (h14 & 31u) + 257;
+			uint32_t ndist = ((h14 >> 5) & 31u) + 1;
+			uint32_t ncode = ((h14 >> 10) & 15u) + 4;
 			bits_drop(b, 14);
 			NEEDOK();
 			if (nlen > 286 || ndist > 30)
 				FAIL(S_DATA_ERROR, D_TOO_MANY_SYMS);
-			sm->cl[lane] = 0;
+			sm->u.h.cl[lane] = 0;
 			__syncwarp();
 			for (uint32_t i = 0; i < ncode; i++) {
 				/* order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15, packed 5 bits each */
@@ -507,46 +637,46 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, 
 				                      : (uint32_t)(ord_hi >> (5 * (i - 12))) & 31u;
 				bits_refill(sm, r, b);
 				if (lane == 0)
-					sm->cl[sym] = (uint8_t)((uint32_t)b.buf & 7u);
+					sm->u.h.cl[sym] = (uint8_t)(bits_peek(b) & 7u);
 				bits_drop(b, 3);
 				NEEDOK();
 			}
 			__syncwarp();
-			int cl_empty;
-			if (build_table(sm, sm->cl, 19, TB_CODES, sm->dist, CL_ROOT, DIST_TABLE, &cl_empty))
+			if (build_table(sm, sm->u.h.cl, 19, TB_CODES, sm->dist, CL_ROOT, DIST_TABLE))
 				FAIL(S_DATA_ERROR, D_BAD_CODELEN_SET);
 			uint32_t have = 0, prev = 0;
 			const uint32_t want = nlen + ndist;
 			while (have < want) {
 				bits_refill(sm, r, b);
-				uint32_t e = sm->dist[(uint32_t)b.buf & ((1u << CL_ROOT) - 1u)];
-				uint32_t sym = E_VAL(e);
-				if (E_KIND(e) == K_INV)
+				uint32_t e = sm->dist[bits_peek(b) & ((1u << CL_ROOT) - 1u)];
+				uint32_t sym = e >> 8;
+				if (e & E_SLOW)
 					sym = 0;    /* zlib quirk: empty code-length code reads as length 0, 1 bit */
-				bits_drop(b, E_TOTAL(e));
+				bits_drop(b, e);
 				NEEDOK();
 				if (sym < 16) {
 					if (lane == 0)
-						sm->lens[have] = (uint8_t)sym;
+						sm->u.h.lens[have] = (uint8_t)sym;
 					prev = sym;
 					have++;
 					continue;
 				}
 				uint32_t copy, fill;
+				uint32_t x = bits_peek(b);
 				if (sym == 16) {
-					copy = 3 + ((uint32_t)b.buf & 3u);
+					copy = 3 + (x & 3u);
 					bits_drop(b, 2);
 					NEEDOK();
 					if (have == 0)
 						FAIL(S_DATA_ERROR, D_BAD_BITLEN_REPEAT);
 					fill = prev;
 				} else if (sym == 17) {
-					copy = 3 + ((uint32_t)b.buf & 7u);
+					copy = 3 + (x & 7u);
 					bits_drop(b, 3);
 					NEEDOK();
 					fill = 0;
 				} else {
-					copy = 11 + ((uint32_t)b.buf & 127u);
+					copy = 11 + (x & 127u);
 					bits_drop(b, 7);
 					NEEDOK();
 					fill = 0;
@@ -554,111 +684,129 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, 
 				if (have + copy > want)
 					FAIL(S_DATA_ERROR, D_BAD_BITLEN_REPEAT);
 				for (uint32_t i = lane; i < copy; i += 32)
-					sm->lens[have + i] = (uint8_t)fill;
+					sm->u.h.lens[have + i] = (uint8_t)fill;
 				prev = fill;
 				have += copy;
 			}
 			__syncwarp();
-			if (sm->lens[256] == 0)
+			if (sm->u.h.lens[256] == 0)
 				FAIL(S_DATA_ERROR, D_NO_EOB);
-			int e0;
-			if (build_table(sm, sm->lens, (int)nlen, TB_LIT, sm->lit, LIT_ROOT, LIT_TABLE, &e0))
+			if (build_table(sm, sm->u.h.lens, (int)nlen, TB_LIT, sm->lit, LIT_ROOT, LIT_TABLE))
 				FAIL(S_DATA_ERROR, D_BAD_LITLEN_SET);
-			if (build_table(sm, sm->lens + nlen, (int)ndist, TB_DIST, sm->dist, DIST_ROOT,
-			    DIST_TABLE, &e0))
+			if (build_table(sm, sm->u.h.lens + nlen, (int)ndist, TB_DIST, sm->dist, DIST_ROOT,
+			    DIST_TABLE))
 				FAIL(S_DATA_ERROR, D_BAD_DIST_SET);
 		}
 
-		/* ---- symbols: batches of up to 32, lane k keeps symbol k ---- */
+		/* ---- symbols, batch after batch ---- */
 		for (;;) {
-			uint32_t my_len = 0, my_val = 0;
-			uint32_t n = 0;
-			int32_t stop = 0;        /* 0 go on, 1 EOB, <0 status, detail in stop_detail */
-			uint32_t stop_detail = 0;
-
-			while (n < 32) {
-				bits_refill(sm, r, b);
-				uint32_t e = lookup(sm->lit, b.buf, LIT_ROOT);
-				uint32_t kind = E_KIND(e);
-				if (kind == K_LIT) {
-					bits_drop(b, E_TOTAL(e));
-					if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
-					if (lane == n) { my_len = 1; my_val = E_VAL(e); }
-					n++;
-					continue;
-				}
-				if (kind == K_BASE) {
-					uint32_t len = E_VAL(e) + (((uint32_t)(b.buf >> E_CLEN(e))) & ((1u << E_EB(e)) - 1u));
-					bits_drop(b, E_TOTAL(e));
-					if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
-					bits_refill(sm, r, b);
-					uint32_t d = lookup(sm->dist, b.buf, DIST_ROOT);
-					if (E_KIND(d) != K_BASE) {
-						/* zlib judges the code with only its own bits */
-						bits_drop(b, E_TOTAL(d));
-						if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
-						stop = S_DATA_ERROR; stop_detail = D_BAD_DIST_CODE;
-						break;
-					}
-					uint32_t dist = E_VAL(d) + (((uint32_t)(b.buf >> E_CLEN(d))) & ((1u << E_EB(d)) - 1u));
-					bits_drop(b, E_TOTAL(d));
-					if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
-					if (lane == n) { my_len = len; my_val = dist; }
-					n++;
-					continue;
-				}
-				bits_drop(b, E_TOTAL(e));
-				if (bits_exhausted(b)) { stop = S_BUF_ERROR; break; }
-				if (kind == K_EOB) { stop = 1; break; }
-				stop = S_DATA_ERROR; stop_detail = D_BAD_LITLEN_CODE;
-				break;
-			}
+			uint32_t my, n, stop_detail = 0;
+			int32_t stop;
+			/* a batch consumes at most 32 x 48 bits = 192 bytes */
+			if (b.rd + 200u <= b.rd_end)
+				stop = decode_batch<false>(sm, r, b, my, n, stop_detail);
+			else
+				stop = decode_batch<true>(sm, r, b, my, n, stop_detail);
 
 			/* ---- resolve the batch ---- */
-			uint32_t len = lane < n ? my_len : 0;
+			uint32_t len = lane < n ? my >> 16 : 0;
+			const uint32_t val = my & 0xffffu;
 			uint32_t incl = len;
 			for (int o = 1; o < 32; o <<= 1) {
 				uint32_t t = __shfl_up_sync(B2I_FULL, incl, o);
 				if ((int)lane >= o) incl += t;
 			}
 			uint32_t rel = incl - len;                /* offset inside the batch */
-			bool is_match = len >= 3;
 			/* first symbol that cannot be written: bad distance or no room */
-			bool far = is_match && my_val > outp + rel;
+			bool far = len >= 3 && val > outp + rel;
 			bool full = len != 0 && (rel + len > cap - outp);
 			unsigned badmask = __ballot_sync(B2I_FULL, far || full);
 			if (badmask) {
 				int first = __ffs(badmask) - 1;
 				bool first_far = __shfl_sync(B2I_FULL, (int)far, first) != 0;
 				n = (uint32_t)first;
-				if (lane >= n) { len = 0; is_match = false; }
+				if (lane >= n) len = 0;
 				stop = first_far ? S_DATA_ERROR : S_OUT_OVERFLOW;
 				stop_detail = first_far ? D_DIST_TOO_FAR : 0;
 			}
-			uint32_t total = __shfl_sync(B2I_FULL, incl, n ? n - 1 : 0);
-			if (n == 0) total = 0;
-			uint8_t *dst = out + outp;
-			if (len == 1)
-				dst[rel] = (uint8_t)my_val;
-			unsigned mm = __ballot_sync(B2I_FULL, is_match);
+			uint32_t T = __shfl_sync(B2I_FULL, incl, n ? n - 1 : 0);
+			if (n == 0) T = 0;
+			const uint32_t c = outp & 15u;
+			uint8_t *stg = sm->u.stage;
+			uint8_t *g16 = out + (outp - c);           /* global address of stg[0] */
+			const uint32_t srel = lane < n ? rel : 0xffffu;
+			const uint32_t pk = (len << 16) | val;
+			if (lane < c)
+				stg[lane] = (uint8_t)carry;
+			/* round 1, one output byte per lane: find the symbol that owns it (binary
+			 * search over the prefix sums), then either take the literal, or fetch
+			 * the source byte from global memory when it was flushed before this
+			 * batch.  Four loads are kept in flight per lane. */
+			for (uint32_t t0 = 0; t0 < T; t0 += 128) {
+				uint32_t v[4];
+				uint32_t di[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const uint32_t t = t0 + 32 * k + lane;
+					uint32_t lo = 0, ro = 0;
+#pragma unroll
+					for (int sft = 16; sft; sft >>= 1) {
+						uint32_t pv = __shfl_sync(B2I_FULL, srel, lo + sft);
+						if (pv <= t) { lo += sft; ro = pv; }
+					}
+					const uint32_t opk = __shfl_sync(B2I_FULL, pk, lo);
+					const uint32_t olen = opk >> 16, oval = opk & 0xffffu;
+					di[k] = 0xffffffffu;
+					v[k] = oval;
+					if (t < T) {
+						if (olen == 1) {
+							di[k] = c + t;
+						} else {
+							uint32_t off = t - ro;
+							if (oval < olen)
+								off %= oval;           /* overlapping copy: period = distance */
+							int sidx = (int)(c + ro + off) - (int)oval;
+							if (sidx < 0) {
+								v[k] = g16[sidx];
+								di[k] = c + t;
+							}
+						}
+					}
+				}
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					if (di[k] != 0xffffffffu)
+						stg[di[k]] = (uint8_t)v[k];
+			}
 			__syncwarp();
+			/* round 2: bytes whose source is still in the staging buffer (the carry
+			 * or this very batch), match by match in stream order */
+			unsigned mm = __ballot_sync(B2I_FULL,
+			    len >= 3 && c + rel + (len < val ? len : val) > val);
 			while (mm) {
 				int src_lane = __ffs(mm) - 1;
 				mm &= mm - 1;
 				uint32_t mrel = __shfl_sync(B2I_FULL, rel, src_lane);
-				uint32_t mlen = __shfl_sync(B2I_FULL, len, src_lane);
-				uint32_t mdist = __shfl_sync(B2I_FULL, my_val, src_lane);
-				uint8_t *d = dst + mrel;
-				if (mdist >= mlen) {
-					for (uint32_t j = lane; j < mlen; j += 32)
-						d[j] = d[(int64_t)j - (int64_t)mdist];
-				} else {
-					for (uint32_t j = lane; j < mlen; j += 32)
-						d[j] = d[(int64_t)(j % mdist) - (int64_t)mdist];
+				uint32_t mpk = __shfl_sync(B2I_FULL, pk, src_lane);
+				uint32_t mlen = mpk >> 16, mdist = mpk & 0xffffu;
+				for (uint32_t j = lane; j < mlen; j += 32) {
+					uint32_t off = mdist < mlen ? j % mdist : j;
+					int sidx = (int)(c + mrel + off) - (int)mdist;
+					if (sidx >= 0)
+						stg[c + mrel + j] = stg[sidx];
 				}
 				__syncwarp();
 			}
-			outp += total;
+			/* flush whole 16-byte units, keep the rest as the new carry */
+			{
+				const uint32_t fill = c + T, groups = fill >> 4;
+				for (uint32_t g = lane; g < groups; g += 32)
+					*(uint4 *)(g16 + 16 * g) = *(const uint4 *)(stg + 16 * g);
+				if (lane < (fill & 15u))
+					carry = stg[16 * groups + lane];
+				__syncwarp();
+			}
+			outp += T;
 			if (stop == 1)
 				break;
 			if (stop < 0)
@@ -666,6 +814,10 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, 
 		}
 	} while (!last);
 done:
+	/* the carry joins the rest of the output (error paths included: whatever was
+	 * produced is in global memory when the warp reports out_bytes) */
+	if (lane < (outp & 15u))
+		out[(outp & ~15u) + lane] = (uint8_t)carry;
 	__syncwarp();
 	/* no bulk copy may still be in flight into this warp's ring when the
 	 * shared memory is handed to the next stream or the CTA exits */
