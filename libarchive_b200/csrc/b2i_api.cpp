@@ -35,6 +35,7 @@ struct b2i_ctx {
 	bool own_stream;
 	uint32_t *d_crc_tab;   /* 1024 */
 	uint32_t *d_xp8;       /* 40 */
+	uint32_t *d_scratch;   /* token regions of the lane-parallel decoder, one per resident warp */
 	uint64_t launches;
 	/* grow-only staging for b2i_decode_host / b2i_crc32 */
 	uint8_t *d_in;  size_t d_in_cap;
@@ -122,6 +123,7 @@ extern "C" int b2i_ctx_create(int device, void *cuda_stream, b2i_ctx **out)
 	}
 	if (cudaMalloc(&c->d_crc_tab, 1024 * 4) != cudaSuccess ||
 	    cudaMalloc(&c->d_xp8, 40 * 4) != cudaSuccess ||
+	    cudaMalloc(&c->d_scratch, b2i_inflate_scratch_bytes(sms)) != cudaSuccess ||
 	    b2i_launch_tables(c->d_crc_tab, c->d_xp8, c->stream) != cudaSuccess ||
 	    cudaStreamSynchronize(c->stream) != cudaSuccess) {
 		b2i_ctx_destroy(c);
@@ -140,6 +142,7 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 	cudaStreamSynchronize(c->stream);
 	cudaFree(c->d_crc_tab);
 	cudaFree(c->d_xp8);
+	cudaFree(c->d_scratch);
 	cudaFree(c->d_in);
 	cudaFree(c->d_out);
 	if (c->own_stream)
@@ -324,7 +327,7 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 		CU(c, cudaMemsetAsync(p->d_counter, 0, 4, c->stream));
 		CU(c, b2i_launch_inflate((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out, p->d_descs,
 		    p->d_results, p->d_order, p->n_deflate, p->d_counter, c->d_crc_tab, c->d_xp8,
-		    c->num_sms, c->stream));
+		    getenv("B2I_UNIFORM_ONLY") ? NULL : c->d_scratch, c->num_sms, c->stream));
 		c->launches++;
 	}
 	if (p->n_stored) {

@@ -23,12 +23,15 @@ extern "C" __global__ void __launch_bounds__(INFLATE_WARPS * 32, 7)
 b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *__restrict__ out,
     const B2iDesc *__restrict__ descs, B2iResult *__restrict__ results,
     const uint32_t *__restrict__ order, uint32_t n, unsigned int *counter,
-    const uint32_t *__restrict__ crc_tab, const uint32_t *__restrict__ xp8)
+    const uint32_t *__restrict__ crc_tab, const uint32_t *__restrict__ xp8, uint32_t *scratch)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
 	const unsigned lane = threadIdx.x & 31;
 	Ring ring;
+	/* token scratch of this warp for the lane-parallel decoder (NULL: uniform only) */
+	uint32_t *my_scratch = scratch ? scratch + (size_t)(blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5)) *
+	    LP_SCRATCH_WORDS : nullptr;
 
 	ring_init(sm, ring);
 	for (;;) {
@@ -40,7 +43,7 @@ b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *_
 			break;
 		const uint32_t idx = order[slot];
 		const B2iDesc d = descs[idx];
-		process_deflate_stream(sm, ring, in, in_total, out, d, &results[idx], crc_tab, xp8);
+		process_deflate_stream(sm, ring, my_scratch, in, in_total, out, d, &results[idx], crc_tab, xp8);
 		__syncwarp();
 	}
 }
@@ -172,6 +175,11 @@ b2i_tables_kernel(uint32_t *crc_tab, uint32_t *xp8)
 /* ---- launch wrappers (called from b2i_api.cpp; plain C++ signatures) ------ */
 
 size_t b2i_inflate_smem_bytes(void) { return sizeof(WarpSmem) * INFLATE_WARPS; }
+/* token scratch for a launch on `num_sms` SMs (every resident warp owns one region) */
+size_t b2i_inflate_scratch_bytes(int num_sms)
+{
+	return (size_t)num_sms * 7u * INFLATE_WARPS * LP_SCRATCH_WORDS * sizeof(uint32_t);
+}
 
 cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, cudaStream_t st)
 {
@@ -181,8 +189,8 @@ cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, cudaStream_t st)
 
 cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out,
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
-    unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, int num_sms,
-    cudaStream_t st)
+    unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
+    int num_sms, cudaStream_t st)
 {
 	static bool configured = false;
 	const size_t smem = b2i_inflate_smem_bytes();
@@ -202,7 +210,7 @@ cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *ou
 	if (blocks > max_blocks)
 		blocks = max_blocks;
 	b2i_inflate_kernel<<<blocks, INFLATE_WARPS * 32, smem, st>>>(in, in_total, out, descs,
-	    results, order, n, counter, crc_tab, xp8);
+	    results, order, n, counter, crc_tab, xp8, scratch);
 	return cudaGetLastError();
 }
 

@@ -527,6 +527,122 @@ B2I_DEV int decode_batch(WarpSmem *sm, Ring &r, Bits &b, uint32_t &my, uint32_t 
 }
 
 /* ------------------------------------------------------------------------ */
+/* batch resolution: symbols -> bytes in global memory                       */
+/* ------------------------------------------------------------------------ */
+/*
+ * Lane k (k < n) holds symbol k as (length << 16 | literal-or-distance).
+ * Appends the batch to the output.  `stop`/`stop_detail` are only written when
+ * a symbol cannot be produced (distance reaches before the start of the
+ * output, or the output capacity is exceeded): the batch is then cut right
+ * before that symbol, exactly where zlib would stop.
+ */
+B2I_DEV void resolve_batch(WarpSmem *sm, uint8_t *out, uint32_t cap, uint32_t &outp, uint32_t &carry,
+    uint32_t my, uint32_t n, int32_t &stop, uint32_t &stop_detail)
+{
+	const unsigned lane = b2i_lane();
+	uint32_t len = lane < n ? my >> 16 : 0;
+	const uint32_t val = my & 0xffffu;
+	uint32_t incl = len;
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t t = __shfl_up_sync(B2I_FULL, incl, o);
+		if ((int)lane >= o) incl += t;
+	}
+	uint32_t rel = incl - len;                /* offset inside the batch */
+	/* first symbol that cannot be written: bad distance or no room */
+	bool far = len >= 3 && val > outp + rel;
+	bool full = len != 0 && (rel + len > cap - outp);
+	unsigned badmask = __ballot_sync(B2I_FULL, far || full);
+	if (badmask) {
+		int first = __ffs(badmask) - 1;
+		bool first_far = __shfl_sync(B2I_FULL, (int)far, first) != 0;
+		n = (uint32_t)first;
+		if (lane >= n) len = 0;
+		stop = first_far ? S_DATA_ERROR : S_OUT_OVERFLOW;
+		stop_detail = first_far ? D_DIST_TOO_FAR : 0;
+	}
+	uint32_t T = __shfl_sync(B2I_FULL, incl, n ? n - 1 : 0);
+	if (n == 0) T = 0;
+	const uint32_t c = outp & 15u;
+	uint8_t *stg = sm->u.stage;
+	uint8_t *g16 = out + (outp - c);           /* global address of stg[0] */
+	const uint32_t srel = lane < n ? rel : 0xffffu;
+	const uint32_t pk = (len << 16) | val;
+	if (lane < c)
+		stg[lane] = (uint8_t)carry;
+	/* round 1, one output byte per lane: find the symbol that owns it (binary
+	 * search over the prefix sums), then either take the literal, or fetch
+	 * the source byte from global memory when it was flushed before this
+	 * batch.  Four loads are kept in flight per lane. */
+	for (uint32_t t0 = 0; t0 < T; t0 += 128) {
+		uint32_t v[4];
+		uint32_t di[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const uint32_t t = t0 + 32 * k + lane;
+			uint32_t lo = 0, ro = 0;
+#pragma unroll
+			for (int sft = 16; sft; sft >>= 1) {
+				uint32_t pv = __shfl_sync(B2I_FULL, srel, lo + sft);
+				if (pv <= t) { lo += sft; ro = pv; }
+			}
+			const uint32_t opk = __shfl_sync(B2I_FULL, pk, lo);
+			const uint32_t olen = opk >> 16, oval = opk & 0xffffu;
+			di[k] = 0xffffffffu;
+			v[k] = oval;
+			if (t < T) {
+				if (olen == 1) {
+					di[k] = c + t;
+				} else {
+					uint32_t off = t - ro;
+					if (oval < olen)
+						off %= oval;           /* overlapping copy: period = distance */
+					int sidx = (int)(c + ro + off) - (int)oval;
+					if (sidx < 0) {
+						v[k] = g16[sidx];
+						di[k] = c + t;
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (di[k] != 0xffffffffu)
+				stg[di[k]] = (uint8_t)v[k];
+	}
+	__syncwarp();
+	/* round 2: bytes whose source is still in the staging buffer (the carry
+	 * or this very batch), match by match in stream order */
+	unsigned mm = __ballot_sync(B2I_FULL,
+	    len >= 3 && c + rel + (len < val ? len : val) > val);
+	while (mm) {
+		int src_lane = __ffs(mm) - 1;
+		mm &= mm - 1;
+		uint32_t mrel = __shfl_sync(B2I_FULL, rel, src_lane);
+		uint32_t mpk = __shfl_sync(B2I_FULL, pk, src_lane);
+		uint32_t mlen = mpk >> 16, mdist = mpk & 0xffffu;
+		for (uint32_t j = lane; j < mlen; j += 32) {
+			uint32_t off = mdist < mlen ? j % mdist : j;
+			int sidx = (int)(c + mrel + off) - (int)mdist;
+			if (sidx >= 0)
+				stg[c + mrel + j] = stg[sidx];
+		}
+		__syncwarp();
+	}
+	/* flush whole 16-byte units, keep the rest as the new carry */
+	{
+		const uint32_t fill = c + T, groups = fill >> 4;
+		for (uint32_t g = lane; g < groups; g += 32)
+			*(uint4 *)(g16 + 16 * g) = *(const uint4 *)(stg + 16 * g);
+		if (lane < (fill & 15u))
+			carry = stg[16 * groups + lane];
+		__syncwarp();
+	}
+	outp += T;
+}
+
+#include "inflate_lp.cuh"
+
+/* ------------------------------------------------------------------------ */
 /* one stream                                                               */
 /* ------------------------------------------------------------------------ */
 struct StreamOut {
@@ -539,8 +655,8 @@ struct StreamOut {
 #define FAIL(st, dt) do { res.status = (st); res.detail = (dt); goto done; } while (0)
 #define NEEDOK() do { if (bits_exhausted(b)) FAIL(S_BUF_ERROR, 0); } while (0)
 
-B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, uint64_t in_total,
-    uint64_t in_off, uint64_t in_len, uint8_t *out, uint64_t out_cap)
+B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, const uint8_t *in_base,
+    uint64_t in_total, uint64_t in_off, uint64_t in_len, uint8_t *out, uint64_t out_cap)
 {
 	const unsigned lane = b2i_lane();
 	StreamOut res;
@@ -698,7 +814,20 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, 
 				FAIL(S_DATA_ERROR, D_BAD_DIST_SET);
 		}
 
-		/* ---- symbols, batch after batch ---- */
+		/* ---- symbols: lane-parallel while the block has enough input left ---- */
+		if (scratch) {
+			uint64_t P = (uint64_t)b.rd * 8 - (uint64_t)(int64_t)b.cnt;   /* bits from gbase */
+			uint32_t det = 0;
+			int st = lp_block(sm, r.gbase, r.glimit, (uint64_t)b.rd_end * 8, P, scratch, out, cap,
+			    outp, carry, det);
+			bits_seek(sm, r, b, (uint32_t)(P >> 3));
+			bits_drop(b, (uint32_t)P & 7u);
+			if (st < 0)
+				FAIL(st, det);
+			if (st == 0)
+				continue;            /* end-of-block consumed: next block header */
+		}
+		/* ---- symbols, batch after batch (warp-uniform) ---- */
 		for (;;) {
 			uint32_t my, n, stop_detail = 0;
 			int32_t stop;
@@ -708,105 +837,7 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, const uint8_t *in_base, 
 			else
 				stop = decode_batch<true>(sm, r, b, my, n, stop_detail);
 
-			/* ---- resolve the batch ---- */
-			uint32_t len = lane < n ? my >> 16 : 0;
-			const uint32_t val = my & 0xffffu;
-			uint32_t incl = len;
-			for (int o = 1; o < 32; o <<= 1) {
-				uint32_t t = __shfl_up_sync(B2I_FULL, incl, o);
-				if ((int)lane >= o) incl += t;
-			}
-			uint32_t rel = incl - len;                /* offset inside the batch */
-			/* first symbol that cannot be written: bad distance or no room */
-			bool far = len >= 3 && val > outp + rel;
-			bool full = len != 0 && (rel + len > cap - outp);
-			unsigned badmask = __ballot_sync(B2I_FULL, far || full);
-			if (badmask) {
-				int first = __ffs(badmask) - 1;
-				bool first_far = __shfl_sync(B2I_FULL, (int)far, first) != 0;
-				n = (uint32_t)first;
-				if (lane >= n) len = 0;
-				stop = first_far ? S_DATA_ERROR : S_OUT_OVERFLOW;
-				stop_detail = first_far ? D_DIST_TOO_FAR : 0;
-			}
-			uint32_t T = __shfl_sync(B2I_FULL, incl, n ? n - 1 : 0);
-			if (n == 0) T = 0;
-			const uint32_t c = outp & 15u;
-			uint8_t *stg = sm->u.stage;
-			uint8_t *g16 = out + (outp - c);           /* global address of stg[0] */
-			const uint32_t srel = lane < n ? rel : 0xffffu;
-			const uint32_t pk = (len << 16) | val;
-			if (lane < c)
-				stg[lane] = (uint8_t)carry;
-			/* round 1, one output byte per lane: find the symbol that owns it (binary
-			 * search over the prefix sums), then either take the literal, or fetch
-			 * the source byte from global memory when it was flushed before this
-			 * batch.  Four loads are kept in flight per lane. */
-			for (uint32_t t0 = 0; t0 < T; t0 += 128) {
-				uint32_t v[4];
-				uint32_t di[4];
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					const uint32_t t = t0 + 32 * k + lane;
-					uint32_t lo = 0, ro = 0;
-#pragma unroll
-					for (int sft = 16; sft; sft >>= 1) {
-						uint32_t pv = __shfl_sync(B2I_FULL, srel, lo + sft);
-						if (pv <= t) { lo += sft; ro = pv; }
-					}
-					const uint32_t opk = __shfl_sync(B2I_FULL, pk, lo);
-					const uint32_t olen = opk >> 16, oval = opk & 0xffffu;
-					di[k] = 0xffffffffu;
-					v[k] = oval;
-					if (t < T) {
-						if (olen == 1) {
-							di[k] = c + t;
-						} else {
-							uint32_t off = t - ro;
-							if (oval < olen)
-								off %= oval;           /* overlapping copy: period = distance */
-							int sidx = (int)(c + ro + off) - (int)oval;
-							if (sidx < 0) {
-								v[k] = g16[sidx];
-								di[k] = c + t;
-							}
-						}
-					}
-				}
-#pragma unroll
-				for (int k = 0; k < 4; k++)
-					if (di[k] != 0xffffffffu)
-						stg[di[k]] = (uint8_t)v[k];
-			}
-			__syncwarp();
-			/* round 2: bytes whose source is still in the staging buffer (the carry
-			 * or this very batch), match by match in stream order */
-			unsigned mm = __ballot_sync(B2I_FULL,
-			    len >= 3 && c + rel + (len < val ? len : val) > val);
-			while (mm) {
-				int src_lane = __ffs(mm) - 1;
-				mm &= mm - 1;
-				uint32_t mrel = __shfl_sync(B2I_FULL, rel, src_lane);
-				uint32_t mpk = __shfl_sync(B2I_FULL, pk, src_lane);
-				uint32_t mlen = mpk >> 16, mdist = mpk & 0xffffu;
-				for (uint32_t j = lane; j < mlen; j += 32) {
-					uint32_t off = mdist < mlen ? j % mdist : j;
-					int sidx = (int)(c + mrel + off) - (int)mdist;
-					if (sidx >= 0)
-						stg[c + mrel + j] = stg[sidx];
-				}
-				__syncwarp();
-			}
-			/* flush whole 16-byte units, keep the rest as the new carry */
-			{
-				const uint32_t fill = c + T, groups = fill >> 4;
-				for (uint32_t g = lane; g < groups; g += 32)
-					*(uint4 *)(g16 + 16 * g) = *(const uint4 *)(stg + 16 * g);
-				if (lane < (fill & 15u))
-					carry = stg[16 * groups + lane];
-				__syncwarp();
-			}
-			outp += T;
+			resolve_batch(sm, out, cap, outp, carry, my, n, stop, stop_detail);
 			if (stop == 1)
 				break;
 			if (stop < 0)

@@ -37,6 +37,7 @@ struct Job {
 	const uint8_t *in; uint64_t in_total; uint8_t *out;
 	B2iDesc d; B2iResult res;
 	int mode; /* 0 inflate+crc, 1 crc of in[in_off, +in_len) */
+	uint32_t *scratch;
 	uint32_t crc_out;
 };
 struct LaneArg { Job *job; unsigned lane; };
@@ -50,7 +51,7 @@ static void *lane_main(void *p)
 	if (j->mode == 0) {
 		Ring ring;
 		ring_init(&j->sm, ring);
-		process_deflate_stream(&j->sm, ring, j->in, j->in_total, j->out, j->d, &j->res, g_crc_tab, g_xp8);
+		process_deflate_stream(&j->sm, ring, j->scratch, j->in, j->in_total, j->out, j->d, &j->res, g_crc_tab, g_xp8);
 	} else {
 		crc_load_tables(j->sm.lit, g_crc_tab);
 		uint32_t raw0 = crc_warp_raw0(j->in + j->d.in_off, j->d.in_len, j->sm.lit, g_xp8);
@@ -70,13 +71,20 @@ static void run(Job *j)
 	pthread_barrier_destroy(&j->warp.bar);
 }
 
+long g_lp_rounds, g_lp_passes;
+extern "C" void emul_lp_stats(long *r, long *p) { *r = g_lp_rounds; *p = g_lp_passes; }
+static int g_use_lp = 1;
+extern "C" void emul_set_lane_parallel(int on) { g_use_lp = on; }
+
 extern "C" int emul_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out, const B2iDesc *d, B2iResult *res)
 {
 	if (!g_tab_ready) make_tables();
 	Job *j = new Job();
 	j->in = in; j->in_total = in_total; j->out = out; j->d = *d; j->mode = 0;
+	j->scratch = g_use_lp ? (uint32_t *)malloc(LP_SCRATCH_WORDS * 4) : NULL;
 	run(j);
 	*res = j->res;
+	free(j->scratch);
 	delete j;
 	return 0;
 }

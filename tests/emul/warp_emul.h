@@ -53,6 +53,7 @@ static inline unsigned __ballot_sync(unsigned, int pred)
 	emul_sync();
 	return r;
 }
+static inline int __any_sync(unsigned m, int pred);
 static inline unsigned __match_any_sync(unsigned, unsigned v)
 {
 	tl_warp->xchg[tl_lane] = v;
@@ -71,6 +72,7 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v)
 	emul_sync();
 	return r;
 }
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
