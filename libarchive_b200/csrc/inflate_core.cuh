@@ -71,6 +71,7 @@
 /* Output staging: a batch of symbols is assembled here and leaves for global
  * memory as aligned 16-byte stores.  It shares its space with the block-header
  * scratch (code lengths, counters), which is only live while a header is parsed. */
+#define SHORT_MAX   8     /* matches up to this long are copied by their own lane */
 #define STAGE_BYTES 832
 #define BATCH_SOFT  559   /* keep decoding while the batch holds <= this many
                              bytes: 15 (carry) + 559 + 258 (one more match) = 832 */
@@ -565,66 +566,52 @@ B2I_DEV void resolve_batch(WarpSmem *sm, uint8_t *out, uint32_t cap, uint32_t &o
 	const uint32_t c = outp & 15u;
 	uint8_t *stg = sm->u.stage;
 	uint8_t *g16 = out + (outp - c);           /* global address of stg[0] */
-	const uint32_t srel = lane < n ? rel : 0xffffu;
 	const uint32_t pk = (len << 16) | val;
 	if (lane < c)
 		stg[lane] = (uint8_t)carry;
-	/* round 1, one output byte per lane: find the symbol that owns it (binary
-	 * search over the prefix sums), then either take the literal, or fetch
-	 * the source byte from global memory when it was flushed before this
-	 * batch.  Four loads are kept in flight per lane. */
-	for (uint32_t t0 = 0; t0 < T; t0 += 128) {
-		uint32_t v[4];
-		uint32_t di[4];
+	/* step 1, every lane for its own symbol: a literal goes straight into the
+	 * staging buffer; a short match whose source does not overlap its target
+	 * fetches the bytes that were flushed to global memory before this batch
+	 * (all loads first, then the stores, so up to SHORT_MAX loads are in
+	 * flight per lane). */
+	const int sbase = (int)(c + rel) - (int)val;   /* staging index of the first source byte */
+	const bool is_match = len >= 3;
+	const bool shortm = is_match && val >= len && len <= SHORT_MAX;
+	uint32_t gl = 0;                                /* leading bytes that come from global memory */
+	if (shortm && sbase < 0)
+		gl = (uint32_t)(-sbase) < len ? (uint32_t)(-sbase) : len;
+	if (len == 1)
+		stg[c + rel] = (uint8_t)val;
+	{
+		uint8_t v[SHORT_MAX];
 #pragma unroll
-		for (int k = 0; k < 4; k++) {
-			const uint32_t t = t0 + 32 * k + lane;
-			uint32_t lo = 0, ro = 0;
+		for (int j = 0; j < SHORT_MAX; j++)
+			if ((uint32_t)j < gl)
+				v[j] = g16[sbase + j];
 #pragma unroll
-			for (int sft = 16; sft; sft >>= 1) {
-				uint32_t pv = __shfl_sync(B2I_FULL, srel, lo + sft);
-				if (pv <= t) { lo += sft; ro = pv; }
-			}
-			const uint32_t opk = __shfl_sync(B2I_FULL, pk, lo);
-			const uint32_t olen = opk >> 16, oval = opk & 0xffffu;
-			di[k] = 0xffffffffu;
-			v[k] = oval;
-			if (t < T) {
-				if (olen == 1) {
-					di[k] = c + t;
-				} else {
-					uint32_t off = t - ro;
-					if (oval < olen)
-						off %= oval;           /* overlapping copy: period = distance */
-					int sidx = (int)(c + ro + off) - (int)oval;
-					if (sidx < 0) {
-						v[k] = g16[sidx];
-						di[k] = c + t;
-					}
-				}
-			}
-		}
-#pragma unroll
-		for (int k = 0; k < 4; k++)
-			if (di[k] != 0xffffffffu)
-				stg[di[k]] = (uint8_t)v[k];
+		for (int j = 0; j < SHORT_MAX; j++)
+			if ((uint32_t)j < gl)
+				stg[c + rel + j] = v[j];
 	}
 	__syncwarp();
-	/* round 2: bytes whose source is still in the staging buffer (the carry
-	 * or this very batch), match by match in stream order */
-	unsigned mm = __ballot_sync(B2I_FULL,
-	    len >= 3 && c + rel + (len < val ? len : val) > val);
+	/* step 2, the whole warp, match by match in stream order: long or overlapping
+	 * matches, and the bytes of short ones whose source is still in the staging
+	 * buffer (the carry or this very batch) */
+	unsigned mm = __ballot_sync(B2I_FULL, is_match && (!shortm || gl < len));
 	while (mm) {
 		int src_lane = __ffs(mm) - 1;
 		mm &= mm - 1;
 		uint32_t mrel = __shfl_sync(B2I_FULL, rel, src_lane);
 		uint32_t mpk = __shfl_sync(B2I_FULL, pk, src_lane);
 		uint32_t mlen = mpk >> 16, mdist = mpk & 0xffffu;
+		const bool mshort = mdist >= mlen && mlen <= SHORT_MAX;   /* global part already done */
 		for (uint32_t j = lane; j < mlen; j += 32) {
-			uint32_t off = mdist < mlen ? j % mdist : j;
+			uint32_t off = mdist < mlen ? j % mdist : j;          /* overlap: period = distance */
 			int sidx = (int)(c + mrel + off) - (int)mdist;
 			if (sidx >= 0)
 				stg[c + mrel + j] = stg[sidx];
+			else if (!mshort)
+				stg[c + mrel + j] = g16[sidx];
 		}
 		__syncwarp();
 	}

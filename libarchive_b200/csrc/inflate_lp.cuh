@@ -69,15 +69,16 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 {
 	const char *litp = (const char *)sm->lit;
 	const char *distp = (const char *)sm->dist;
-	uint32_t lo = 0, hi = 0, widx = start >> 5, ns = 0, tm = LT_NONE, ex = 0;
+	uint32_t lo = 0, hi = 0, widx = start >> 5, ns = 0, tm = LT_NONE, ex = 0, nw = 0;
 	int32_t cnt = 0;
 	bool active = run;
 
+/* the word after the one being consumed is always already on its way (nw) */
+#define LP_FETCH(i_) gw[(wbase + (i_)) < max_word ? (wbase + (i_)) : max_word]
 #define LP_LOAD() do { \
-		uint32_t wi_ = wbase + widx; \
-		uint32_t w_ = gw[wi_ < max_word ? wi_ : max_word]; \
-		uint64_t W_ = (((uint64_t)hi << 32) | lo) | ((uint64_t)w_ << (cnt + 2)); \
+		uint64_t W_ = (((uint64_t)hi << 32) | lo) | ((uint64_t)nw << (cnt + 2)); \
 		lo = (uint32_t)W_; hi = (uint32_t)(W_ >> 32); cnt += 32; widx++; \
+		nw = LP_FETCH(widx); \
 	} while (0)
 #define LP_DROP(n_) do { \
 		uint32_t n__ = (n_); \
@@ -85,6 +86,7 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 	} while (0)
 
 	if (active) {
+		nw = LP_FETCH(widx);
 		LP_LOAD();
 		LP_DROP(start & 31u);
 	}
@@ -148,6 +150,7 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 		}
 	}
 #undef LP_LOAD
+#undef LP_FETCH
 #undef LP_DROP
 	if (run) {
 		o.exit = ex;
