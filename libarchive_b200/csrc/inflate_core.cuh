@@ -71,10 +71,10 @@
 /* Output staging: a batch of symbols is assembled here and leaves for global
  * memory as aligned 16-byte stores.  It shares its space with the block-header
  * scratch (code lengths, counters), which is only live while a header is parsed. */
-#define SHORT_MAX   8     /* matches up to this long are copied by their own lane */
-#define STAGE_BYTES 832
-#define BATCH_SOFT  559   /* keep decoding while the batch holds <= this many
-                             bytes: 15 (carry) + 559 + 258 (one more match) = 832 */
+#define STAGE_BYTES 704
+#define STAGE_WORDS (STAGE_BYTES / 32)   /* words of the one-bit-per-byte owner bitmap */
+#define BATCH_SOFT  431   /* keep decoding while the batch holds <= this many
+                             bytes: 15 (carry) + 431 + 258 (one more match) = 704 */
 struct HeaderScratch {
 	uint8_t  lens[320];
 	uint16_t cnt[16];
@@ -90,6 +90,8 @@ struct __align__(16) WarpSmem {
 		uint8_t stage[STAGE_BYTES];
 	} u;
 	unsigned long long mbar[2];
+	uint32_t bm[STAGE_WORDS];   /* batch resolution: bit s set = a symbol starts at staging byte s */
+	uint8_t  wp[24];            /* symbols that start in earlier bitmap words */
 };
 
 /* ------------------------------------------------------------------------ */
@@ -537,7 +539,10 @@ B2I_DEV int decode_batch(WarpSmem *sm, Ring &r, Bits &b, uint32_t &my, uint32_t 
  * output, or the output capacity is exceeded): the batch is then cut right
  * before that symbol, exactly where zlib would stop.
  */
-B2I_DEV void resolve_batch(WarpSmem *sm, uint8_t *out, uint32_t cap, uint32_t &outp, uint32_t &carry,
+#ifdef B2I_HOST_EMUL
+extern long g_stat_hist[64], g_stat_instage, g_stat_overlap, g_stat_batches, g_stat_bytes, g_stat_syms;
+#endif
+B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint32_t cap, uint32_t &outp, uint32_t &carry,
     uint32_t my, uint32_t n, int32_t &stop, uint32_t &stop_detail)
 {
 	const unsigned lane = b2i_lane();
@@ -549,6 +554,11 @@ B2I_DEV void resolve_batch(WarpSmem *sm, uint8_t *out, uint32_t cap, uint32_t &o
 		if ((int)lane >= o) incl += t;
 	}
 	uint32_t rel = incl - len;                /* offset inside the batch */
+	/* take symbols while the batch holds <= BATCH_SOFT bytes (what decode_batch
+	 * guarantees by construction; pre-decoded token runs are cut here) */
+	n = (uint32_t)__popc(__ballot_sync(B2I_FULL, len != 0 && rel <= BATCH_SOFT));
+	if (lane >= n) len = 0;
+	const uint32_t taken = n;
 	/* first symbol that cannot be written: bad distance or no room */
 	bool far = len >= 3 && val > outp + rel;
 	bool full = len != 0 && (rel + len > cap - outp);
@@ -567,51 +577,89 @@ B2I_DEV void resolve_batch(WarpSmem *sm, uint8_t *out, uint32_t cap, uint32_t &o
 	uint8_t *stg = sm->u.stage;
 	uint8_t *g16 = out + (outp - c);           /* global address of stg[0] */
 	const uint32_t pk = (len << 16) | val;
+#ifdef B2I_HOST_EMUL
+	if (lane < n) {
+		__sync_fetch_and_add(&g_stat_hist[len > 63 ? 63 : len], 1);
+		if (len >= 3 && (int)(c + rel) - (int)val + (int)(len < val ? len : val) > 0) __sync_fetch_and_add(&g_stat_instage, 1);
+		if (len >= 3 && val < len) __sync_fetch_and_add(&g_stat_overlap, 1);
+	}
+	if (lane == 0) { g_stat_batches++; g_stat_bytes += T; g_stat_syms += n; }
+#endif
+	/* Which symbol owns staging byte s?  Every symbol sets the bit of its first
+	 * byte in a bitmap; the owner of s is (number of set bits at or below s) - 1,
+	 * i.e. one popcount plus a per-word running count. */
+	if (lane < STAGE_WORDS)
+		sm->bm[lane] = 0;
 	if (lane < c)
 		stg[lane] = (uint8_t)carry;
-	/* step 1, every lane for its own symbol: a literal goes straight into the
-	 * staging buffer; a short match whose source does not overlap its target
-	 * fetches the bytes that were flushed to global memory before this batch
-	 * (all loads first, then the stores, so up to SHORT_MAX loads are in
-	 * flight per lane). */
-	const int sbase = (int)(c + rel) - (int)val;   /* staging index of the first source byte */
-	const bool is_match = len >= 3;
-	const bool shortm = is_match && val >= len && len <= SHORT_MAX;
-	uint32_t gl = 0;                                /* leading bytes that come from global memory */
-	if (shortm && sbase < 0)
-		gl = (uint32_t)(-sbase) < len ? (uint32_t)(-sbase) : len;
-	if (len == 1)
-		stg[c + rel] = (uint8_t)val;
+	__syncwarp();
+	if (len != 0)
+		atomicOr(&sm->bm[(c + rel) >> 5], 1u << ((c + rel) & 31u));
+	__syncwarp();
 	{
-		uint8_t v[SHORT_MAX];
-#pragma unroll
-		for (int j = 0; j < SHORT_MAX; j++)
-			if ((uint32_t)j < gl)
-				v[j] = g16[sbase + j];
-#pragma unroll
-		for (int j = 0; j < SHORT_MAX; j++)
-			if ((uint32_t)j < gl)
-				stg[c + rel + j] = v[j];
+		uint32_t pc = lane < STAGE_WORDS ? (uint32_t)__popc(sm->bm[lane]) : 0, inc = pc;
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t t = __shfl_up_sync(B2I_FULL, inc, o);
+			if ((int)lane >= o) inc += t;
+		}
+		if (lane < STAGE_WORDS)
+			sm->wp[lane] = (uint8_t)(inc - pc);
 	}
 	__syncwarp();
-	/* step 2, the whole warp, match by match in stream order: long or overlapping
-	 * matches, and the bytes of short ones whose source is still in the staging
-	 * buffer (the carry or this very batch) */
-	unsigned mm = __ballot_sync(B2I_FULL, is_match && (!shortm || gl < len));
+	/* round 1, one output byte per lane: a literal is stored as is, a match byte
+	 * whose source was flushed to global memory before this batch is fetched
+	 * (four loads in flight per lane); sources inside the staging buffer wait
+	 * for round 2. */
+	for (uint32_t t0 = 0; t0 < T; t0 += 128) {
+		uint32_t v[4];
+		uint32_t di[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const uint32_t t = t0 + 32 * k + lane;
+			const uint32_t si = t < T ? c + t : c;          /* staging index */
+			const uint32_t own = (uint32_t)sm->wp[si >> 5] +
+			    (uint32_t)__popc(sm->bm[si >> 5] & (0xffffffffu >> (31u - (si & 31u)))) - 1u;
+			const uint32_t opk = __shfl_sync(B2I_FULL, pk, own);
+			const uint32_t ro = __shfl_sync(B2I_FULL, rel, own);
+			const uint32_t olen = opk >> 16, oval = opk & 0xffffu;
+			di[k] = 0xffffffffu;
+			v[k] = oval;
+			if (t < T) {
+				if (olen == 1) {
+					di[k] = si;
+				} else {
+					uint32_t off = t - ro;
+					if (oval < olen)
+						off %= oval;           /* overlapping copy: period = distance */
+					int sidx = (int)(c + ro + off) - (int)oval;
+					if (sidx < 0) {
+						v[k] = g16[sidx];
+						di[k] = si;
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (di[k] != 0xffffffffu)
+				stg[di[k]] = (uint8_t)v[k];
+	}
+	__syncwarp();
+	/* round 2: bytes whose source is still in the staging buffer (the carry
+	 * or this very batch), match by match in stream order */
+	unsigned mm = __ballot_sync(B2I_FULL,
+	    len >= 3 && c + rel + (len < val ? len : val) > val);
 	while (mm) {
 		int src_lane = __ffs(mm) - 1;
 		mm &= mm - 1;
 		uint32_t mrel = __shfl_sync(B2I_FULL, rel, src_lane);
 		uint32_t mpk = __shfl_sync(B2I_FULL, pk, src_lane);
 		uint32_t mlen = mpk >> 16, mdist = mpk & 0xffffu;
-		const bool mshort = mdist >= mlen && mlen <= SHORT_MAX;   /* global part already done */
 		for (uint32_t j = lane; j < mlen; j += 32) {
-			uint32_t off = mdist < mlen ? j % mdist : j;          /* overlap: period = distance */
+			uint32_t off = mdist < mlen ? j % mdist : j;
 			int sidx = (int)(c + mrel + off) - (int)mdist;
 			if (sidx >= 0)
 				stg[c + mrel + j] = stg[sidx];
-			else if (!mshort)
-				stg[c + mrel + j] = g16[sidx];
 		}
 		__syncwarp();
 	}
@@ -625,6 +673,7 @@ B2I_DEV void resolve_batch(WarpSmem *sm, uint8_t *out, uint32_t cap, uint32_t &o
 		__syncwarp();
 	}
 	outp += T;
+	return taken;
 }
 
 #include "inflate_lp.cuh"

@@ -226,16 +226,10 @@ B2I_DEV int lp_block(WarpSmem *sm, const uint8_t *gbase, uint64_t glimit, uint64
 			uint32_t j = 0;
 			while (j < cnt) {
 				uint32_t my = j + lane < cnt ? rt[j + lane] : 0;
-				/* as many symbols as the staging buffer takes (same rule as decode_batch) */
-				uint32_t len = my >> 16, incl = len;
-				for (int s = 1; s < 32; s <<= 1) {
-					uint32_t t = __shfl_up_sync(B2I_FULL, incl, s);
-					if ((int)lane >= s) incl += t;
-				}
-				uint32_t n = (uint32_t)__popc(__ballot_sync(B2I_FULL,
-				    j + lane < cnt && incl - len <= BATCH_SOFT));
+				uint32_t avail = cnt - j < 32u ? cnt - j : 32u;
 				int32_t stop = 0;
-				resolve_batch(sm, out, cap, outp, carry, my, n, stop, detail);
+				/* resolve_batch takes as many symbols as its staging buffer holds */
+				uint32_t n = resolve_batch(sm, out, cap, outp, carry, my, avail, stop, detail);
 				if (stop < 0) {
 					P = (uint64_t)wbase * 32u + mexit;
 					return stop;

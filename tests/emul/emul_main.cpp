@@ -72,6 +72,8 @@ static void run(Job *j)
 }
 
 long g_lp_rounds, g_lp_passes;
+long g_stat_hist[64], g_stat_instage, g_stat_overlap, g_stat_batches, g_stat_bytes, g_stat_syms;
+extern "C" void emul_stats(long *h, long *o) { for (int i=0;i<64;i++) h[i]=g_stat_hist[i]; o[0]=g_stat_instage;o[1]=g_stat_overlap;o[2]=g_stat_batches;o[3]=g_stat_bytes;o[4]=g_stat_syms; }
 extern "C" void emul_lp_stats(long *r, long *p) { *r = g_lp_rounds; *p = g_lp_passes; }
 static int g_use_lp = 1;
 extern "C" void emul_set_lane_parallel(int on) { g_use_lp = on; }

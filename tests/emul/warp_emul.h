@@ -73,6 +73,7 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v)
 	return r;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { return __sync_fetch_and_or(p, v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
