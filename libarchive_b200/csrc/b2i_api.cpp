@@ -35,6 +35,8 @@ struct b2i_ctx {
 	bool own_stream;
 	uint32_t *d_crc_tab;   /* 1024 */
 	uint32_t *d_xp8;       /* 40 */
+	uint32_t *d_ztab;      /* 1024: advance-by-512-bytes tables */
+	uint32_t *d_lane_mul;  /* 32 */
 	uint32_t *d_scratch;   /* token regions of the lane-parallel decoder, one per resident warp */
 	uint64_t launches;
 	/* grow-only staging for b2i_decode_host / b2i_crc32 */
@@ -123,8 +125,10 @@ extern "C" int b2i_ctx_create(int device, void *cuda_stream, b2i_ctx **out)
 	}
 	if (cudaMalloc(&c->d_crc_tab, 1024 * 4) != cudaSuccess ||
 	    cudaMalloc(&c->d_xp8, 40 * 4) != cudaSuccess ||
+	    cudaMalloc(&c->d_ztab, 1024 * 4) != cudaSuccess ||
+	    cudaMalloc(&c->d_lane_mul, 32 * 4) != cudaSuccess ||
 	    cudaMalloc(&c->d_scratch, b2i_inflate_scratch_bytes(sms)) != cudaSuccess ||
-	    b2i_launch_tables(c->d_crc_tab, c->d_xp8, c->stream) != cudaSuccess ||
+	    b2i_launch_tables(c->d_crc_tab, c->d_xp8, c->d_ztab, c->d_lane_mul, c->stream) != cudaSuccess ||
 	    cudaStreamSynchronize(c->stream) != cudaSuccess) {
 		b2i_ctx_destroy(c);
 		return B2I_E_CUDA;
@@ -143,6 +147,8 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 	cudaFree(c->d_crc_tab);
 	cudaFree(c->d_xp8);
 	cudaFree(c->d_scratch);
+	cudaFree(c->d_ztab);
+	cudaFree(c->d_lane_mul);
 	cudaFree(c->d_in);
 	cudaFree(c->d_out);
 	if (c->own_stream)
@@ -229,13 +235,23 @@ extern "C" int b2i_plan_create(b2i_ctx *c, const b2i_stream_desc *descs, size_t 
 			e.entry = (uint32_t)i;
 			e.first_work = (uint32_t)work.size();
 			e.pad = 0;
-			for (uint64_t rel = 0; rel < d.in_len; rel += B2I_CRC_CHUNK) {
+			/* pieces: a head up to 16-byte alignment of the input offset, streaming
+			 * pieces of up to 32 KiB in multiples of 512 bytes, and a tail */
+			auto push = [&](uint64_t rel, uint64_t len) {
 				B2iCrcWork w;
 				w.rel = rel;
-				w.len = (uint32_t)std::min<uint64_t>(B2I_CRC_CHUNK, d.in_len - rel);
+				w.len = (uint32_t)len;
 				w.entry = (uint32_t)i;
 				work.push_back(w);
+			};
+			uint64_t rel = 0, left = d.in_len;
+			uint64_t head = std::min<uint64_t>((0 - d.in_off) & 15, left);
+			if (head) { push(rel, head); rel += head; left -= head; }
+			while (left >= 512) {
+				uint64_t len = std::min<uint64_t>(B2I_CRC_CHUNK, left & ~(uint64_t)511);
+				push(rel, len); rel += len; left -= len;
 			}
+			if (left) push(rel, left);
 			e.nwork = (uint32_t)work.size() - e.first_work;
 			ents.push_back(e);
 			max_in = std::max<uint64_t>(max_in, d.in_off + d.in_len);
@@ -333,7 +349,8 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 	if (p->n_stored) {
 		if (p->n_work) {
 			CU(c, b2i_launch_crc_chunks((const uint8_t *)d_in, (uint8_t *)d_out, p->d_descs, p->d_work,
-			    p->n_work, p->d_partial, c->d_crc_tab, c->d_xp8, c->num_sms, c->stream));
+			    p->n_work, p->d_partial, c->d_crc_tab, c->d_xp8, c->d_ztab, c->d_lane_mul, c->num_sms,
+			    c->stream));
 			c->launches++;
 		}
 		CU(c, b2i_launch_crc_combine(p->d_descs, p->d_results, p->d_ents, p->n_stored, p->d_work,

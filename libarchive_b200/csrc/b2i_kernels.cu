@@ -50,27 +50,87 @@ b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *_
 
 /* ---- stored entries ------------------------------------------------------ */
 
-extern "C" __global__ void __launch_bounds__(256)
+/*
+ * K2: CRC-32 of stored entries, one warp per work item, persistent CTAs (one
+ * per SM, 32 warps).  A work item whose bytes are 16-byte aligned and a
+ * multiple of 512 long takes the streaming path:
+ *
+ *   every warp load is one coalesced 512-byte line group (16 bytes per lane);
+ *   each lane runs FOUR independent word streams (the k-th word of its uint4,
+ *   stride 512 bytes): u <- u * x^4096 mod P  ^  word, i.e. four table
+ *   look-ups per word in tables Z0..Z3 (byte j of u advanced by 512 bytes).
+ *   The tables are replicated 32 times in shared memory, [table][byte][lane],
+ *   so lane l only ever touches bank l: no bank conflicts at random indices.
+ *   At the end the four streams of a lane are folded with three ordinary
+ *   4-byte steps, each lane's value is multiplied by its position constant
+ *   x^(32 + 128*(31-lane)) and the warp XOR-reduces.
+ *
+ * Anything else (heads, tails, small entries) takes the generic lane-slice
+ * routine crc_warp_raw0.  Both produce raw0 of the piece; the combine kernel
+ * shifts every partial by the bytes that follow it.
+ */
+#define CRC_THREADS 1024
+#define ZREP_WORDS (4 * 256 * 32)
+
+extern "C" __global__ void __launch_bounds__(CRC_THREADS, 1)
 b2i_crc_chunks_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
     const B2iDesc *__restrict__ descs, const B2iCrcWork *__restrict__ work, uint32_t nwork,
     uint32_t *__restrict__ partial, const uint32_t *__restrict__ crc_tab,
-    const uint32_t *__restrict__ xp8)
+    const uint32_t *__restrict__ xp8, const uint32_t *__restrict__ ztab,
+    const uint32_t *__restrict__ lane_mul)
 {
+	extern __shared__ __align__(16) uint32_t zrep[];       /* [4][256][32] */
 	__shared__ uint32_t tab[1024];
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned warps_per_block = blockDim.x >> 5;
 
 	for (int i = threadIdx.x; i < 1024; i += blockDim.x)
 		tab[i] = crc_tab[i];
+	for (int i = threadIdx.x; i < ZREP_WORDS; i += blockDim.x)
+		zrep[i] = ztab[i >> 5];
 	__syncthreads();
+	const char *zl = (const char *)zrep + lane * 4;            /* this lane's bank */
+	const uint32_t my_mul = lane_mul[lane];
+
 	for (uint32_t w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < nwork;
 	    w += gridDim.x * warps_per_block) {
 		const B2iCrcWork k = work[w];
 		const B2iDesc d = descs[k.entry];
 		const uint8_t *src = in + d.in_off + k.rel;
 		uint32_t raw0 = 0;
-		if (!(d.flags & F_NO_CRC))
-			raw0 = crc_warp_raw0(src, k.len, tab, xp8);
+		if (!(d.flags & F_NO_CRC)) {
+			if ((((uintptr_t)src & 15) | (k.len & 511)) == 0 && k.len) {
+				const uint4 *q = (const uint4 *)src + lane;
+				uint32_t u0 = 0, u1 = 0, u2 = 0, u3 = 0;
+				const uint32_t iters = k.len >> 9;
+#define ZSTEP(u, word) do { \
+		uint32_t a0 = (u << 7) & 0x7f80u, a1 = (u >> 1) & 0x7f80u, \
+		    a2 = (u >> 9) & 0x7f80u, a3 = (u >> 17) & 0x7f80u; \
+		u = *(const uint32_t *)(zl + a0) ^ *(const uint32_t *)(zl + 32768 + a1) ^ \
+		    *(const uint32_t *)(zl + 65536 + a2) ^ *(const uint32_t *)(zl + 98304 + a3) ^ (word); \
+	} while (0)
+#pragma unroll 2
+				for (uint32_t it = 0; it < iters; it++) {
+					const uint4 v = __ldg(q);
+					q += 32;
+					ZSTEP(u0, v.x);
+					ZSTEP(u1, v.y);
+					ZSTEP(u2, v.z);
+					ZSTEP(u3, v.w);
+				}
+#undef ZSTEP
+				/* fold the lane's four streams (4 bytes apart), then place the lane */
+				uint32_t v = crc_word(u0, 0, tab) ^ u1;
+				v = crc_word(v, 0, tab) ^ u2;
+				v = crc_word(v, 0, tab) ^ u3;
+				v = crc_mulmod(v, my_mul);
+				for (int o = 16; o; o >>= 1)
+					v ^= __shfl_xor_sync(B2I_FULL, v, o);
+				raw0 = v;
+			} else {
+				raw0 = crc_warp_raw0(src, k.len, tab, xp8);
+			}
+		}
 		if (lane == 0)
 			partial[w] = raw0;
 		if (!(d.flags & F_NO_COPY)) {
@@ -149,7 +209,7 @@ b2i_unsupported_kernel(const B2iDesc *__restrict__ descs, B2iResult *__restrict_
 
 /* one block of 256 threads: tab[k*256+b] and xp8[k] = x^(8*2^k) */
 extern "C" __global__ void
-b2i_tables_kernel(uint32_t *crc_tab, uint32_t *xp8)
+b2i_tables_kernel(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, uint32_t *lane_mul)
 {
 	__shared__ uint32_t t0[256];
 	const uint32_t b = threadIdx.x;
@@ -170,6 +230,15 @@ b2i_tables_kernel(uint32_t *crc_tab, uint32_t *xp8)
 			p = crc_mulmod(p, p);
 		}
 	}
+	__syncthreads();
+	__threadfence();
+	/* ztab[j*256 + b] = (b << 8j) * x^4096 mod P: byte j of a register advanced by 512 bytes */
+	const uint32_t x4096 = xp8[9];
+	for (int j = 0; j < 4; j++)
+		ztab[j * 256 + b] = crc_mulmod(b << (8 * j), x4096);
+	/* lane_mul[l] = x^(32 + 128*(31-l)): 4 + 16*(31-l) bytes */
+	if (b < 32)
+		lane_mul[b] = crc_xpow8(4u + 16u * (31u - b), xp8);
 }
 
 /* ---- launch wrappers (called from b2i_api.cpp; plain C++ signatures) ------ */
@@ -181,9 +250,10 @@ size_t b2i_inflate_scratch_bytes(int num_sms)
 	return (size_t)num_sms * 7u * INFLATE_WARPS * LP_SCRATCH_WORDS * sizeof(uint32_t);
 }
 
-cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, cudaStream_t st)
+cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, uint32_t *lane_mul,
+    cudaStream_t st)
 {
-	b2i_tables_kernel<<<1, 256, 0, st>>>(crc_tab, xp8);
+	b2i_tables_kernel<<<1, 256, 0, st>>>(crc_tab, xp8, ztab, lane_mul);
 	return cudaGetLastError();
 }
 
@@ -216,13 +286,22 @@ cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *ou
 
 cudaError_t b2i_launch_crc_chunks(const uint8_t *in, uint8_t *out, const B2iDesc *descs,
     const B2iCrcWork *work, uint32_t nwork, uint32_t *partial, const uint32_t *crc_tab,
-    const uint32_t *xp8, int num_sms, cudaStream_t st)
+    const uint32_t *xp8, const uint32_t *ztab, const uint32_t *lane_mul, int num_sms, cudaStream_t st)
 {
-	uint32_t blocks = (nwork + 7) / 8;
-	uint32_t max_blocks = (uint32_t)num_sms * 8u;
-	if (blocks > max_blocks)
-		blocks = max_blocks;
-	b2i_crc_chunks_kernel<<<blocks, 256, 0, st>>>(in, out, descs, work, nwork, partial, crc_tab, xp8);
+	static bool configured = false;
+	const size_t smem = ZREP_WORDS * sizeof(uint32_t);
+	if (!configured) {
+		cudaError_t e = cudaFuncSetAttribute(b2i_crc_chunks_kernel,
+		    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess)
+			return e;
+		configured = true;
+	}
+	uint32_t blocks = (nwork + 31) / 32;
+	if (blocks > (uint32_t)num_sms)
+		blocks = (uint32_t)num_sms;
+	b2i_crc_chunks_kernel<<<blocks, CRC_THREADS, smem, st>>>(in, out, descs, work, nwork, partial,
+	    crc_tab, xp8, ztab, lane_mul);
 	return cudaGetLastError();
 }
 

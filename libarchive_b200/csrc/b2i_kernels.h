@@ -16,18 +16,19 @@ struct B2iCrcEntry {
 	uint32_t nwork;
 	uint32_t pad;
 };
-#define B2I_CRC_CHUNK (16u * 1024u)
+#define B2I_CRC_CHUNK (32u * 1024u)   /* streaming pieces: 16-byte aligned, multiples of 512 bytes */
 
 size_t b2i_inflate_smem_bytes(void);
 size_t b2i_inflate_scratch_bytes(int num_sms);
-cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, cudaStream_t st);
+cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, uint32_t *lane_mul,
+    cudaStream_t st);
 cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out,
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
     int num_sms, cudaStream_t st);
 cudaError_t b2i_launch_crc_chunks(const uint8_t *in, uint8_t *out, const B2iDesc *descs,
     const B2iCrcWork *work, uint32_t nwork, uint32_t *partial, const uint32_t *crc_tab,
-    const uint32_t *xp8, int num_sms, cudaStream_t st);
+    const uint32_t *xp8, const uint32_t *ztab, const uint32_t *lane_mul, int num_sms, cudaStream_t st);
 cudaError_t b2i_launch_crc_combine(const B2iDesc *descs, B2iResult *results,
     const B2iCrcEntry *ents, uint32_t nents, const B2iCrcWork *work, const uint32_t *partial,
     const uint32_t *xp8, cudaStream_t st);
