@@ -109,8 +109,17 @@ b2i_crc_chunks_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
 		u = *(const uint32_t *)(zl + a0) ^ *(const uint32_t *)(zl + 32768 + a1) ^ \
 		    *(const uint32_t *)(zl + 65536 + a2) ^ *(const uint32_t *)(zl + 98304 + a3) ^ (word); \
 	} while (0)
-#pragma unroll 2
-				for (uint32_t it = 0; it < iters; it++) {
+				/* four 512-byte groups per trip, their loads issued before the first use */
+				uint32_t it = 0;
+				for (; it + 4 <= iters; it += 4) {
+					const uint4 v0 = __ldg(q), v1 = __ldg(q + 32), v2 = __ldg(q + 64), v3 = __ldg(q + 96);
+					q += 128;
+					ZSTEP(u0, v0.x); ZSTEP(u1, v0.y); ZSTEP(u2, v0.z); ZSTEP(u3, v0.w);
+					ZSTEP(u0, v1.x); ZSTEP(u1, v1.y); ZSTEP(u2, v1.z); ZSTEP(u3, v1.w);
+					ZSTEP(u0, v2.x); ZSTEP(u1, v2.y); ZSTEP(u2, v2.z); ZSTEP(u3, v2.w);
+					ZSTEP(u0, v3.x); ZSTEP(u1, v3.y); ZSTEP(u2, v3.z); ZSTEP(u3, v3.w);
+				}
+				for (; it < iters; it++) {
 					const uint4 v = __ldg(q);
 					q += 32;
 					ZSTEP(u0, v.x);
