@@ -27,6 +27,8 @@ static_assert(offsetof(b2i_stream_result, detail) == offsetof(B2iResult, detail)
 
 /* per-stream limits of this build: 32-bit positions inside one stream */
 #define B2I_MAX_STREAM_BYTES 0xFFFF0000ull
+#define B2I_PIPE_STREAMS 4
+#define B2I_PIPE_SLICES  8
 
 struct b2i_ctx {
 	int device;
@@ -37,11 +39,18 @@ struct b2i_ctx {
 	uint32_t *d_xp8;       /* 40 */
 	uint32_t *d_ztab;      /* 1024: advance-by-512-bytes tables */
 	uint32_t *d_lane_mul;  /* 32 */
+	unsigned int *d_slot_busy;   /* one flag per token region */
 	uint32_t *d_scratch;   /* token regions of the lane-parallel decoder, one per resident warp */
 	uint64_t launches;
 	/* grow-only staging for b2i_decode_host / b2i_crc32 */
 	uint8_t *d_in;  size_t d_in_cap;
 	uint8_t *d_out; size_t d_out_cap;
+	/* pipelined host path: copy-in / compute / copy-out streams, and a reusable
+	 * (grow-only) arena for the slice plans so that no call allocates */
+	cudaStream_t s_in, s_out, s_cmp[B2I_PIPE_STREAMS];
+	cudaEvent_t ev_in[B2I_PIPE_SLICES], ev_k[B2I_PIPE_SLICES], ev_free;
+	bool pipe_ready;
+	uint8_t *arena_d; uint8_t *arena_h; size_t arena_cap;
 	char err[256];
 };
 
@@ -64,6 +73,8 @@ struct b2i_plan {
 	/* pinned host mirror used for upload and result download */
 	uint8_t *h_block;
 	size_t block_bytes, results_off;
+	cudaStream_t stream;     /* where this plan's upload, kernels and result copy run */
+	bool owns_memory;        /* false: d_block / h_block live in the context's arena */
 };
 
 static int fail(b2i_ctx *c, int code, const char *fmt, ...)
@@ -128,6 +139,8 @@ extern "C" int b2i_ctx_create(int device, void *cuda_stream, b2i_ctx **out)
 	    cudaMalloc(&c->d_ztab, 1024 * 4) != cudaSuccess ||
 	    cudaMalloc(&c->d_lane_mul, 32 * 4) != cudaSuccess ||
 	    cudaMalloc(&c->d_scratch, b2i_inflate_scratch_bytes(sms)) != cudaSuccess ||
+	    cudaMalloc(&c->d_slot_busy, b2i_inflate_scratch_slots(sms) * 4) != cudaSuccess ||
+	    cudaMemset(c->d_slot_busy, 0, b2i_inflate_scratch_slots(sms) * 4) != cudaSuccess ||
 	    b2i_launch_tables(c->d_crc_tab, c->d_xp8, c->d_ztab, c->d_lane_mul, c->stream) != cudaSuccess ||
 	    cudaStreamSynchronize(c->stream) != cudaSuccess) {
 		b2i_ctx_destroy(c);
@@ -147,10 +160,20 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 	cudaFree(c->d_crc_tab);
 	cudaFree(c->d_xp8);
 	cudaFree(c->d_scratch);
+	cudaFree(c->d_slot_busy);
 	cudaFree(c->d_ztab);
 	cudaFree(c->d_lane_mul);
 	cudaFree(c->d_in);
 	cudaFree(c->d_out);
+	cudaFree(c->arena_d);
+	cudaFreeHost(c->arena_h);
+	if (c->pipe_ready) {
+		cudaStreamDestroy(c->s_in);
+		cudaStreamDestroy(c->s_out);
+		for (int i = 0; i < B2I_PIPE_STREAMS; i++) cudaStreamDestroy(c->s_cmp[i]);
+		for (int i = 0; i < B2I_PIPE_SLICES; i++) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_k[i]); }
+		cudaEventDestroy(c->ev_free);
+	}
 	if (c->own_stream)
 		cudaStreamDestroy(c->stream);
 	delete c;
@@ -207,7 +230,17 @@ extern "C" int b2i_memcpy_d2h(b2i_ctx *c, void *dst, const void *src, size_t byt
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
 
-extern "C" int b2i_plan_create(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, b2i_plan **out)
+static size_t plan_block_bound(size_t n, size_t stored_bytes)
+{
+	/* generous upper bound of the block b2i_plan_build lays out for n streams */
+	size_t works = stored_bytes / 512 + 3 * n + 8;
+	return n * (sizeof(B2iDesc) + sizeof(B2iResult) + 8 + sizeof(B2iCrcEntry)) +
+	    works * (sizeof(B2iCrcWork) + 4) + 16 * 256;
+}
+
+/* mem_d / mem_h: caller-provided (arena) memory of mem_cap bytes, or NULL to allocate */
+static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cudaStream_t stream,
+    uint8_t *mem_d, uint8_t *mem_h, size_t mem_cap, b2i_plan **out)
 {
 	if (c == NULL || out == NULL || (n && descs == NULL) || n > 0x7fffffffu)
 		return fail(c, B2I_E_INVAL, "b2i_plan_create: bad arguments");
@@ -279,6 +312,8 @@ extern "C" int b2i_plan_create(b2i_ctx *c, const b2i_stream_desc *descs, size_t 
 	p->need_aligned_in = !deflate.empty();
 	p->max_in_end = max_in;
 	p->max_out_end = max_out;
+	p->stream = stream;
+	p->owns_memory = (mem_d == NULL);
 
 	size_t off = 0;
 	const size_t o_descs = off;   off = align_up(off + n * sizeof(B2iDesc), 256);
@@ -293,7 +328,14 @@ extern "C" int b2i_plan_create(b2i_ctx *c, const b2i_stream_desc *descs, size_t 
 	p->block_bytes = off;
 	p->results_off = o_results;
 
-	if (cudaMalloc(&p->d_block, off ? off : 256) != cudaSuccess ||
+	if (mem_d != NULL) {
+		if (off > mem_cap) {
+			delete p;
+			return fail(c, B2I_E_NOMEM, "plan arena too small (%zu > %zu)", off, mem_cap);
+		}
+		p->d_block = mem_d;
+		p->h_block = mem_h;
+	} else if (cudaMalloc(&p->d_block, off ? off : 256) != cudaSuccess ||
 	    cudaHostAlloc((void **)&p->h_block, off ? off : 256, cudaHostAllocDefault) != cudaSuccess) {
 		b2i_plan_destroy(p);
 		return fail(c, B2I_E_NOMEM, "plan allocation of %zu bytes failed", off);
@@ -312,13 +354,20 @@ extern "C" int b2i_plan_create(b2i_ctx *c, const b2i_stream_desc *descs, size_t 
 	if (!work.empty()) memcpy(p->h_block + o_work, work.data(), work.size() * sizeof(B2iCrcWork));
 	if (!ents.empty()) memcpy(p->h_block + o_ents, ents.data(), ents.size() * sizeof(B2iCrcEntry));
 	if (!unsup.empty()) memcpy(p->h_block + o_unsup, unsup.data(), unsup.size() * 4);
-	cudaError_t e = cudaMemcpyAsync(p->d_block, p->h_block, upload_bytes, cudaMemcpyHostToDevice, c->stream);
+	cudaError_t e = cudaMemcpyAsync(p->d_block, p->h_block, upload_bytes, cudaMemcpyHostToDevice, stream);
 	if (e != cudaSuccess) {
 		b2i_plan_destroy(p);
 		return fail(c, B2I_E_CUDA, "plan upload: %s", cudaGetErrorString(e));
 	}
 	*out = p;
 	return B2I_OK;
+}
+
+extern "C" int b2i_plan_create(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, b2i_plan **out)
+{
+	if (c == NULL)
+		return B2I_E_INVAL;
+	return b2i_plan_build(c, descs, n, c->stream, NULL, NULL, 0, out);
 }
 
 extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, void *d_out, size_t out_bytes)
@@ -340,25 +389,25 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 		return fail(c, B2I_E_INVAL, "d_out must be 16-byte aligned");
 	CU(c, cudaSetDevice(c->device));
 	if (p->n_deflate) {
-		CU(c, cudaMemsetAsync(p->d_counter, 0, 4, c->stream));
+		CU(c, cudaMemsetAsync(p->d_counter, 0, 4, p->stream));
 		CU(c, b2i_launch_inflate((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out, p->d_descs,
 		    p->d_results, p->d_order, p->n_deflate, p->d_counter, c->d_crc_tab, c->d_xp8,
-		    getenv("B2I_UNIFORM_ONLY") ? NULL : c->d_scratch, c->num_sms, c->stream));
+		    getenv("B2I_UNIFORM_ONLY") ? NULL : c->d_scratch, c->d_slot_busy, c->num_sms, p->stream));
 		c->launches++;
 	}
 	if (p->n_stored) {
 		if (p->n_work) {
 			CU(c, b2i_launch_crc_chunks((const uint8_t *)d_in, (uint8_t *)d_out, p->d_descs, p->d_work,
 			    p->n_work, p->d_partial, c->d_crc_tab, c->d_xp8, c->d_ztab, c->d_lane_mul, c->num_sms,
-			    c->stream));
+			    p->stream));
 			c->launches++;
 		}
 		CU(c, b2i_launch_crc_combine(p->d_descs, p->d_results, p->d_ents, p->n_stored, p->d_work,
-		    p->d_partial, c->d_xp8, c->stream));
+		    p->d_partial, c->d_xp8, p->stream));
 		c->launches++;
 	}
 	if (p->n_unsup) {
-		CU(c, b2i_launch_unsupported(p->d_descs, p->d_results, p->d_unsup, p->n_unsup, c->stream));
+		CU(c, b2i_launch_unsupported(p->d_descs, p->d_results, p->d_unsup, p->n_unsup, p->stream));
 		c->launches++;
 	}
 	return B2I_OK;
@@ -372,8 +421,8 @@ extern "C" int b2i_plan_results(b2i_plan *p, b2i_stream_result *res)
 	if (p->n == 0)
 		return B2I_OK;
 	CU(c, cudaMemcpyAsync(p->h_block + p->results_off, p->d_results, p->n * sizeof(B2iResult),
-	    cudaMemcpyDeviceToHost, c->stream));
-	CU(c, cudaStreamSynchronize(c->stream));
+	    cudaMemcpyDeviceToHost, p->stream));
+	CU(c, cudaStreamSynchronize(p->stream));
 	memcpy(res, p->h_block + p->results_off, p->n * sizeof(B2iResult));
 	return B2I_OK;
 }
@@ -383,9 +432,11 @@ extern "C" void b2i_plan_destroy(b2i_plan *p)
 	if (p == NULL)
 		return;
 	cudaSetDevice(p->ctx->device);
-	cudaStreamSynchronize(p->ctx->stream);
-	cudaFree(p->d_block);
-	cudaFreeHost(p->h_block);
+	cudaStreamSynchronize(p->stream);
+	if (p->owns_memory) {
+		cudaFree(p->d_block);
+		cudaFreeHost(p->h_block);
+	}
 	delete p;
 }
 
@@ -412,6 +463,47 @@ static int ensure_dev(b2i_ctx *c, uint8_t **buf, size_t *cap, size_t need)
 	return B2I_OK;
 }
 
+static int ensure_pipe(b2i_ctx *c)
+{
+	if (c->pipe_ready)
+		return B2I_OK;
+	CU(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+	CU(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+	for (int i = 0; i < B2I_PIPE_STREAMS; i++)
+		CU(c, cudaStreamCreateWithFlags(&c->s_cmp[i], cudaStreamNonBlocking));
+	for (int i = 0; i < B2I_PIPE_SLICES; i++) {
+		CU(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+		CU(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+	}
+	CU(c, cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming));
+	c->pipe_ready = true;
+	return B2I_OK;
+}
+
+static int ensure_arena(b2i_ctx *c, size_t need)
+{
+	if (c->arena_cap >= need)
+		return B2I_OK;
+	cudaDeviceSynchronize();
+	cudaFree(c->arena_d);
+	cudaFreeHost(c->arena_h);
+	c->arena_d = NULL; c->arena_h = NULL; c->arena_cap = 0;
+	need += need / 2;
+	if (cudaMalloc(&c->arena_d, need) != cudaSuccess ||
+	    cudaHostAlloc((void **)&c->arena_h, need, cudaHostAllocDefault) != cudaSuccess)
+		return fail(c, B2I_E_NOMEM, "plan arena of %zu bytes", need);
+	c->arena_cap = need;
+	return B2I_OK;
+}
+
+/*
+ * Host buffers in, host buffers out.  The descriptors are cut into up to
+ * B2I_PIPE_SLICES contiguous slices of equal weight; slice s is copied in on
+ * the copy-in stream, decoded on a compute stream as soon as its bytes have
+ * landed (the slice kernels are small enough to be co-resident), and copied
+ * out on the copy-out stream as soon as its kernel is done - so H2D of slice
+ * s+1, the kernel of slice s and D2H of slice s-1 overlap.  Synchronous.
+ */
 extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
     const b2i_stream_desc *descs, size_t n, void *host_out, size_t out_bytes,
     b2i_stream_result *res)
@@ -428,40 +520,120 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		return rc;
 	if ((rc = ensure_dev(c, &c->d_out, &c->d_out_cap, out_bytes)) != B2I_OK)
 		return rc;
-	b2i_plan *p = NULL;
-	if ((rc = b2i_plan_create(c, descs, n, &p)) != B2I_OK)
+	if ((rc = ensure_pipe(c)) != B2I_OK)
 		return rc;
-	/* only the span the streams actually touch crosses the host link */
-	uint64_t lo = ~0ull, hi = 0;
+
+	/* slices: contiguous descriptor ranges of about equal csize + usize */
+	uint64_t total_w = 0, stored_bytes = 0;
 	for (size_t i = 0; i < n; i++) {
-		if (descs[i].method != B2I_METHOD_DEFLATE && descs[i].method != B2I_METHOD_STORED)
+		total_w += descs[i].in_len + descs[i].out_cap;
+		if (descs[i].method == B2I_METHOD_STORED)
+			stored_bytes += descs[i].in_len;
+		if ((descs[i].method == B2I_METHOD_DEFLATE || descs[i].method == B2I_METHOD_STORED) &&
+		    descs[i].in_off + descs[i].in_len > in_bytes)
+			return fail(c, B2I_E_INVAL, "a stream extends past the input buffer");
+	}
+	size_t K = (size_t)std::min<uint64_t>(B2I_PIPE_SLICES, std::max<uint64_t>(1, total_w / (32u << 20)));
+	if (n < 16 * K)
+		K = 1;
+	size_t cut[B2I_PIPE_SLICES + 1];
+	{
+		uint64_t acc = 0;
+		size_t k = 1;
+		cut[0] = 0;
+		for (size_t i = 0; i < n && k < K; i++) {
+			acc += descs[i].in_len + descs[i].out_cap;
+			if (acc >= total_w * k / K)
+				cut[k++] = i + 1;
+		}
+		while (k <= K)
+			cut[k++] = n;
+	}
+	const size_t per_slice = plan_block_bound(n, stored_bytes);      /* each slice <= whole */
+	size_t arena_need = 0;
+	size_t arena_off[B2I_PIPE_SLICES];
+	for (size_t s = 0; s < K; s++) {
+		arena_off[s] = arena_need;
+		arena_need += align_up(plan_block_bound(cut[s + 1] - cut[s], stored_bytes), 256);
+	}
+	(void)per_slice;
+	if ((rc = ensure_arena(c, arena_need)) != B2I_OK)
+		return rc;
+	/* work of an earlier call on the caller's stream (if any) comes first */
+	CU(c, cudaEventRecord(c->ev_free, c->stream));
+	CU(c, cudaStreamWaitEvent(c->s_in, c->ev_free, 0));
+
+	b2i_plan *plans[B2I_PIPE_SLICES] = { 0 };
+	rc = B2I_OK;
+	for (size_t s = 0; s < K && rc == B2I_OK; s++) {
+		const b2i_stream_desc *sd = descs + cut[s];
+		const size_t sn = cut[s + 1] - cut[s];
+		cudaStream_t cs = c->s_cmp[s % B2I_PIPE_STREAMS];
+		if (sn == 0)
 			continue;
-		lo = std::min<uint64_t>(lo, descs[i].in_off);
-		hi = std::max<uint64_t>(hi, descs[i].in_off + descs[i].in_len);
-	}
-	if (hi > in_bytes) {
-		b2i_plan_destroy(p);
-		return fail(c, B2I_E_INVAL, "a stream extends past the input buffer");
-	}
-	if (lo < hi) {
-		lo &= ~(uint64_t)15;
-		cudaError_t e = cudaMemcpyAsync(c->d_in + lo, (const uint8_t *)host_in + lo, hi - lo,
-		    cudaMemcpyHostToDevice, c->stream);
-		if (e != cudaSuccess) {
-			b2i_plan_destroy(p);
-			return fail(c, B2I_E_CUDA, "H2D: %s", cudaGetErrorString(e));
+		uint64_t lo = ~0ull, hi = 0;
+		for (size_t i = 0; i < sn; i++) {
+			if (sd[i].method != B2I_METHOD_DEFLATE && sd[i].method != B2I_METHOD_STORED)
+				continue;
+			lo = std::min<uint64_t>(lo, sd[i].in_off);
+			hi = std::max<uint64_t>(hi, sd[i].in_off + sd[i].in_len);
+		}
+		if (lo < hi) {
+			lo &= ~(uint64_t)15;
+			cudaError_t e = cudaMemcpyAsync(c->d_in + lo, (const uint8_t *)host_in + lo, hi - lo,
+			    cudaMemcpyHostToDevice, c->s_in);
+			if (e != cudaSuccess) { rc = fail(c, B2I_E_CUDA, "H2D: %s", cudaGetErrorString(e)); break; }
+		}
+		if (cudaEventRecord(c->ev_in[s], c->s_in) != cudaSuccess ||
+		    cudaStreamWaitEvent(cs, c->ev_in[s], 0) != cudaSuccess) {
+			rc = fail(c, B2I_E_CUDA, "event"); break;
+		}
+		rc = b2i_plan_build(c, sd, sn, cs, c->arena_d + arena_off[s], c->arena_h + arena_off[s],
+		    align_up(plan_block_bound(sn, stored_bytes), 256), &plans[s]);
+		if (rc != B2I_OK)
+			break;
+		rc = b2i_plan_launch(plans[s], c->d_in, in_bytes, c->d_out, out_bytes);
+		if (rc != B2I_OK)
+			break;
+		/* results of the slice ride on the compute stream right behind its kernels */
+		if (cudaMemcpyAsync(plans[s]->h_block + plans[s]->results_off, plans[s]->d_results,
+		    sn * sizeof(B2iResult), cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+		    cudaEventRecord(c->ev_k[s], cs) != cudaSuccess ||
+		    cudaStreamWaitEvent(c->s_out, c->ev_k[s], 0) != cudaSuccess) {
+			rc = fail(c, B2I_E_CUDA, "event"); break;
+		}
+		if (host_out != NULL && plans[s]->max_out_end) {
+			uint64_t olo = ~0ull, ohi = 0;
+			for (size_t i = 0; i < sn; i++) {
+				if (sd[i].method == B2I_METHOD_DEFLATE ||
+				    (sd[i].method == B2I_METHOD_STORED && !(sd[i].flags & B2I_F_NO_COPY))) {
+					olo = std::min<uint64_t>(olo, sd[i].out_off);
+					ohi = std::max<uint64_t>(ohi, sd[i].out_off + sd[i].out_cap);
+				}
+			}
+			if (olo < ohi && ohi <= out_bytes) {
+				cudaError_t e = cudaMemcpyAsync((uint8_t *)host_out + olo, c->d_out + olo, ohi - olo,
+				    cudaMemcpyDeviceToHost, c->s_out);
+				if (e != cudaSuccess) { rc = fail(c, B2I_E_CUDA, "D2H: %s", cudaGetErrorString(e)); break; }
+			}
 		}
 	}
-	rc = b2i_plan_launch(p, c->d_in, in_bytes, c->d_out, out_bytes);
-	if (rc == B2I_OK && host_out != NULL && p->max_out_end) {
-		cudaError_t e = cudaMemcpyAsync(host_out, c->d_out, (size_t)p->max_out_end,
-		    cudaMemcpyDeviceToHost, c->stream);
-		if (e != cudaSuccess)
-			rc = fail(c, B2I_E_CUDA, "D2H: %s", cudaGetErrorString(e));
+	/* everything funnels into the copy-out stream (it waited on every slice's kernel) */
+	cudaError_t e1 = cudaStreamSynchronize(c->s_out);
+	cudaError_t e2 = cudaStreamSynchronize(c->s_in);
+	for (int i = 0; i < B2I_PIPE_STREAMS; i++)
+		if (cudaStreamSynchronize(c->s_cmp[i]) != cudaSuccess)
+			e1 = cudaErrorUnknown;
+	if (rc == B2I_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
+		rc = fail(c, B2I_E_CUDA, "pipeline: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+	for (size_t s = 0; s < K; s++) {
+		if (plans[s] == NULL)
+			continue;
+		if (rc == B2I_OK)
+			memcpy(res + cut[s], plans[s]->h_block + plans[s]->results_off,
+			    (cut[s + 1] - cut[s]) * sizeof(B2iResult));
+		b2i_plan_destroy(plans[s]);
 	}
-	if (rc == B2I_OK)
-		rc = b2i_plan_results(p, res);
-	b2i_plan_destroy(p);
 	return rc;
 }
 

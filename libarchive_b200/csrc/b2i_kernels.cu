@@ -23,15 +23,30 @@ extern "C" __global__ void __launch_bounds__(INFLATE_WARPS * 32, 7)
 b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *__restrict__ out,
     const B2iDesc *__restrict__ descs, B2iResult *__restrict__ results,
     const uint32_t *__restrict__ order, uint32_t n, unsigned int *counter,
-    const uint32_t *__restrict__ crc_tab, const uint32_t *__restrict__ xp8, uint32_t *scratch)
+    const uint32_t *__restrict__ crc_tab, const uint32_t *__restrict__ xp8, uint32_t *scratch,
+    unsigned int *slot_busy, uint32_t nslots)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
 	const unsigned lane = threadIdx.x & 31;
 	Ring ring;
-	/* token scratch of this warp for the lane-parallel decoder (NULL: uniform only) */
-	uint32_t *my_scratch = scratch ? scratch + (size_t)(blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5)) *
-	    LP_SCRATCH_WORDS : nullptr;
+	/* Token scratch for the lane-parallel decoder (NULL: uniform only).  Several
+	 * launches may be resident at once (pipelined host path), so a warp claims a
+	 * free region for its lifetime: there are twice as many regions as warps
+	 * that fit on the device, probing starts at a per-SM, per-warp position. */
+	uint32_t *my_scratch = nullptr;
+	uint32_t slot = 0;
+	if (scratch) {
+		if (lane == 0) {
+			unsigned smid;
+			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+			slot = (smid * 56u + (blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5)) % 56u) % nslots;
+			while (atomicCAS(&slot_busy[slot], 0u, 1u) != 0u)
+				slot = slot + 1 == nslots ? 0 : slot + 1;
+		}
+		slot = __shfl_sync(B2I_FULL, slot, 0);
+		my_scratch = scratch + (size_t)slot * LP_SCRATCH_WORDS;
+	}
 
 	ring_init(sm, ring);
 	for (;;) {
@@ -45,6 +60,10 @@ b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *_
 		const B2iDesc d = descs[idx];
 		process_deflate_stream(sm, ring, my_scratch, in, in_total, out, d, &results[idx], crc_tab, xp8);
 		__syncwarp();
+	}
+	if (scratch && lane == 0) {
+		__threadfence();
+		atomicExch(&slot_busy[slot], 0u);
 	}
 }
 
@@ -254,9 +273,10 @@ b2i_tables_kernel(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, uint32_t *la
 
 size_t b2i_inflate_smem_bytes(void) { return sizeof(WarpSmem) * INFLATE_WARPS; }
 /* token scratch for a launch on `num_sms` SMs (every resident warp owns one region) */
+uint32_t b2i_inflate_scratch_slots(int num_sms) { return (uint32_t)num_sms * 56u; }
 size_t b2i_inflate_scratch_bytes(int num_sms)
 {
-	return (size_t)num_sms * 7u * INFLATE_WARPS * LP_SCRATCH_WORDS * sizeof(uint32_t);
+	return (size_t)b2i_inflate_scratch_slots(num_sms) * LP_SCRATCH_WORDS * sizeof(uint32_t);
 }
 
 cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, uint32_t *lane_mul,
@@ -269,7 +289,7 @@ cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, 
 cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out,
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
-    int num_sms, cudaStream_t st)
+    unsigned int *slot_busy, int num_sms, cudaStream_t st)
 {
 	static bool configured = false;
 	const size_t smem = b2i_inflate_smem_bytes();
@@ -289,7 +309,7 @@ cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *ou
 	if (blocks > max_blocks)
 		blocks = max_blocks;
 	b2i_inflate_kernel<<<blocks, INFLATE_WARPS * 32, smem, st>>>(in, in_total, out, descs,
-	    results, order, n, counter, crc_tab, xp8, scratch);
+	    results, order, n, counter, crc_tab, xp8, scratch, slot_busy, b2i_inflate_scratch_slots(num_sms));
 	return cudaGetLastError();
 }
 

@@ -20,12 +20,13 @@ struct B2iCrcEntry {
 
 size_t b2i_inflate_smem_bytes(void);
 size_t b2i_inflate_scratch_bytes(int num_sms);
+uint32_t b2i_inflate_scratch_slots(int num_sms);
 cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, uint32_t *lane_mul,
     cudaStream_t st);
 cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out,
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
-    int num_sms, cudaStream_t st);
+    unsigned int *slot_busy, int num_sms, cudaStream_t st);
 cudaError_t b2i_launch_crc_chunks(const uint8_t *in, uint8_t *out, const B2iDesc *descs,
     const B2iCrcWork *work, uint32_t nwork, uint32_t *partial, const uint32_t *crc_tab,
     const uint32_t *xp8, const uint32_t *ztab, const uint32_t *lane_mul, int num_sms, cudaStream_t st);
