@@ -317,6 +317,23 @@ def main():
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
     total_ms = evs[0].elapsed_time(evs[K])
 
+    # ---- host link: pinned H2D / D2H bandwidth for this workload's sizes ------------
+    def link_gbs(fn, nbytes, reps=5):
+        best = 0.0
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+        return best
+    h2d_gbs = link_gbs(lambda: ctx._check(L.b2i_memcpy_h2d(ctx.h, d_in, h_in, in_bytes)), in_bytes)
+    d2h_gbs = link_gbs(lambda: ctx._check(L.b2i_memcpy_d2h(ctx.h, h_out, d_out, max(out_bytes, 1))), max(out_bytes, 1))
+    # a serial copy-in + copy-out of this step's bytes is the host-link floor of one step
+    link_floor_ms = (csize / (h2d_gbs * 1e9) + out_bytes / (d2h_gbs * 1e9)) * 1e3
+    overlap_floor_ms = max(csize / (h2d_gbs * 1e9), out_bytes / (d2h_gbs * 1e9)) * 1e3
+
     # ---- end-to-end timing (host buffers, copies inside) -------------------------
     for _ in range(min(W, 3)):
         e2e_step()
@@ -373,7 +390,11 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms,
                      "out_frac_of_hbm": (usize / (kern_ms * 1e-3) / 1e9) / peak},
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": csize + n * 48,
-                "d2h_bytes_per_step": out_bytes + n * 32, "ms_per_step": e2e_ms / K},
+                "d2h_bytes_per_step": out_bytes + n * 32, "ms_per_step": e2e_ms / K,
+                "host_link": {"h2d_GBps": h2d_gbs, "d2h_GBps": d2h_gbs,
+                              "frac_of_link": overlap_floor_ms / (e2e_ms / K),
+                              "note": "frac = time the slower direction alone needs at the measured pinned "
+                                      "bandwidth / measured e2e step time"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -172,3 +172,31 @@ def test_many_streams_one_pass(ctx):
         assert res[k].status == 0 and res[k].flags == 0 or k >= 0 and res[k].status == 0
         assert res[k].crc == ores[k].crc and res[k].out_bytes == ores[k].out_bytes
     assert gout[:descs[-1].out_off + caps[-1]] == oout[:descs[-1].out_off + caps[-1]]
+
+
+def test_fuzz_garbage_and_mutations(ctx):
+    """Arbitrary bytes never hang or fault the kernel and always classify like zlib:
+    pure garbage, garbage behind a valid dynamic header, and multi-bit mutations of
+    long (lane-parallel sized) streams."""
+    rng = np.random.default_rng(77)
+    txt = synth.synth_text(200000, 13)
+    base = [synth.deflate_raw(txt[:70000], 6), synth.deflate_raw(txt[:70000], 6, zlib.Z_FIXED),
+            synth.deflate_raw(txt, 9), synth.random_dynamic_stream(5, 20000)]
+    streams, names = [], []
+    for k in range(300):
+        n = int(rng.integers(1, 3000))
+        streams.append(rng.integers(0, 256, n, dtype=np.uint8).tobytes()); names.append("garbage%d" % k)
+    for k in range(400):
+        s = bytearray(base[k % len(base)])
+        for _ in range(int(rng.integers(1, 6))):
+            pos = int(rng.integers(0, len(s) * 8))
+            s[pos >> 3] ^= 1 << (pos & 7)
+        if k % 5 == 0:
+            s = s[:int(rng.integers(1, len(s)))]
+        streams.append(bytes(s)); names.append("mut%d" % k)
+    hdr = base[0][:120]
+    for k in range(100):
+        streams.append(hdr + rng.integers(0, 256, int(rng.integers(600, 6000)), dtype=np.uint8).tobytes())
+        names.append("hdr+garbage%d" % k)
+    out = run_streams(ctx, streams, caps=[1 << 18] * len(streams), lead=2, gap=5)
+    compare(names, *out)
