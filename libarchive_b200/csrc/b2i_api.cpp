@@ -75,6 +75,7 @@ struct b2i_plan {
 	size_t block_bytes, results_off;
 	cudaStream_t stream;     /* where this plan's upload, kernels and result copy run */
 	bool owns_memory;        /* false: d_block / h_block live in the context's arena */
+	uint8_t *out_mirror;     /* host-mapped twin of the output (inflated bytes are stored to both) */
 };
 
 static int fail(b2i_ctx *c, int code, const char *fmt, ...)
@@ -390,7 +391,7 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 	CU(c, cudaSetDevice(c->device));
 	if (p->n_deflate) {
 		CU(c, cudaMemsetAsync(p->d_counter, 0, 4, p->stream));
-		CU(c, b2i_launch_inflate((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out, p->d_descs,
+		CU(c, b2i_launch_inflate((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out, p->out_mirror, p->d_descs,
 		    p->d_results, p->d_order, p->n_deflate, p->d_counter, c->d_crc_tab, c->d_xp8,
 		    getenv("B2I_UNIFORM_ONLY") ? NULL : c->d_scratch, c->d_slot_busy, c->num_sms, p->stream));
 		c->launches++;
@@ -534,6 +535,11 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 			return fail(c, B2I_E_INVAL, "a stream extends past the input buffer");
 	}
 	size_t K = (size_t)std::min<uint64_t>(B2I_PIPE_SLICES, std::max<uint64_t>(1, total_w / (32u << 20)));
+	if (const char *ek = getenv("B2I_PIPE_SLICES")) {        /* tuning knob */
+		int v = atoi(ek);
+		if (v >= 1 && v <= B2I_PIPE_SLICES)
+			K = (size_t)v;
+	}
 	if (n < 16 * K)
 		K = 1;
 	size_t cut[B2I_PIPE_SLICES + 1];
@@ -563,6 +569,22 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 	CU(c, cudaEventRecord(c->ev_free, c->stream));
 	CU(c, cudaStreamWaitEvent(c->s_in, c->ev_free, 0));
 
+	/* When host_out is pinned (device-accessible) the inflate kernel stores every
+	 * 16-byte unit to it as well, so decoded bytes cross the host link while the
+	 * kernel is still running instead of in a copy pass afterwards.  Stored
+	 * entries that want a copy keep the copy pass. */
+	uint8_t *mirror = NULL;
+	if (host_out != NULL && getenv("B2I_NO_MIRROR") == NULL) {
+		cudaPointerAttributes pa;
+		if (cudaPointerGetAttributes(&pa, host_out) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+		    pa.devicePointer != NULL)
+			mirror = (uint8_t *)pa.devicePointer;
+		else
+			cudaGetLastError();
+		for (size_t i = 0; i < n && mirror; i++)
+			if (descs[i].method == B2I_METHOD_STORED && !(descs[i].flags & B2I_F_NO_COPY))
+				mirror = NULL;
+	}
 	b2i_plan *plans[B2I_PIPE_SLICES] = { 0 };
 	rc = B2I_OK;
 	for (size_t s = 0; s < K && rc == B2I_OK; s++) {
@@ -592,6 +614,7 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		    align_up(plan_block_bound(sn, stored_bytes), 256), &plans[s]);
 		if (rc != B2I_OK)
 			break;
+		plans[s]->out_mirror = mirror;
 		rc = b2i_plan_launch(plans[s], c->d_in, in_bytes, c->d_out, out_bytes);
 		if (rc != B2I_OK)
 			break;
@@ -602,7 +625,7 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		    cudaStreamWaitEvent(c->s_out, c->ev_k[s], 0) != cudaSuccess) {
 			rc = fail(c, B2I_E_CUDA, "event"); break;
 		}
-		if (host_out != NULL && plans[s]->max_out_end) {
+		if (host_out != NULL && mirror == NULL && plans[s]->max_out_end) {
 			uint64_t olo = ~0ull, ohi = 0;
 			for (size_t i = 0; i < sn; i++) {
 				if (sd[i].method == B2I_METHOD_DEFLATE ||

@@ -21,6 +21,7 @@
 
 extern "C" __global__ void __launch_bounds__(INFLATE_WARPS * 32, 7)
 b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *__restrict__ out,
+    uint8_t *__restrict__ out_mirror,
     const B2iDesc *__restrict__ descs, B2iResult *__restrict__ results,
     const uint32_t *__restrict__ order, uint32_t n, unsigned int *counter,
     const uint32_t *__restrict__ crc_tab, const uint32_t *__restrict__ xp8, uint32_t *scratch,
@@ -58,7 +59,7 @@ b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *_
 			break;
 		const uint32_t idx = order[slot];
 		const B2iDesc d = descs[idx];
-		process_deflate_stream(sm, ring, my_scratch, in, in_total, out, d, &results[idx], crc_tab, xp8);
+		process_deflate_stream(sm, ring, my_scratch, in, in_total, out, out_mirror, d, &results[idx], crc_tab, xp8);
 		__syncwarp();
 	}
 	if (scratch && lane == 0) {
@@ -286,7 +287,7 @@ cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, 
 	return cudaGetLastError();
 }
 
-cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out,
+cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out, uint8_t *out_mirror,
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
     unsigned int *slot_busy, int num_sms, cudaStream_t st)
@@ -308,7 +309,7 @@ cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *ou
 	uint32_t max_blocks = (uint32_t)num_sms * 7u;
 	if (blocks > max_blocks)
 		blocks = max_blocks;
-	b2i_inflate_kernel<<<blocks, INFLATE_WARPS * 32, smem, st>>>(in, in_total, out, descs,
+	b2i_inflate_kernel<<<blocks, INFLATE_WARPS * 32, smem, st>>>(in, in_total, out, out_mirror, descs,
 	    results, order, n, counter, crc_tab, xp8, scratch, slot_busy, b2i_inflate_scratch_slots(num_sms));
 	return cudaGetLastError();
 }

@@ -23,7 +23,7 @@ size_t b2i_inflate_scratch_bytes(int num_sms);
 uint32_t b2i_inflate_scratch_slots(int num_sms);
 cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, uint32_t *lane_mul,
     cudaStream_t st);
-cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out,
+cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out, uint8_t *out_mirror,
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
     unsigned int *slot_busy, int num_sms, cudaStream_t st);

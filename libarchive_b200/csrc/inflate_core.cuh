@@ -542,7 +542,7 @@ B2I_DEV int decode_batch(WarpSmem *sm, Ring &r, Bits &b, uint32_t &my, uint32_t 
 #ifdef B2I_HOST_EMUL
 extern long g_stat_hist[64], g_stat_instage, g_stat_overlap, g_stat_batches, g_stat_bytes, g_stat_syms;
 #endif
-B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint32_t cap, uint32_t &outp, uint32_t &carry,
+B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_t cap, uint32_t &outp, uint32_t &carry,
     uint32_t my, uint32_t n, int32_t &stop, uint32_t &stop_detail)
 {
 	const unsigned lane = b2i_lane();
@@ -666,8 +666,12 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint32_t cap, uint32_
 	/* flush whole 16-byte units, keep the rest as the new carry */
 	{
 		const uint32_t fill = c + T, groups = fill >> 4;
-		for (uint32_t g = lane; g < groups; g += 32)
-			*(uint4 *)(g16 + 16 * g) = *(const uint4 *)(stg + 16 * g);
+		for (uint32_t g = lane; g < groups; g += 32) {
+			const uint4 v16 = *(const uint4 *)(stg + 16 * g);
+			*(uint4 *)(g16 + 16 * g) = v16;
+			if (mir)            /* host-mapped copy of the output: no separate D2H pass */
+				*(uint4 *)(mir + (outp - c) + 16 * g) = v16;
+		}
 		if (lane < (fill & 15u))
 			carry = stg[16 * groups + lane];
 		__syncwarp();
@@ -692,7 +696,7 @@ struct StreamOut {
 #define NEEDOK() do { if (bits_exhausted(b)) FAIL(S_BUF_ERROR, 0); } while (0)
 
 B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, const uint8_t *in_base,
-    uint64_t in_total, uint64_t in_off, uint64_t in_len, uint8_t *out, uint64_t out_cap)
+    uint64_t in_total, uint64_t in_off, uint64_t in_len, uint8_t *out, uint8_t *mir, uint64_t out_cap)
 {
 	const unsigned lane = b2i_lane();
 	StreamOut res;
@@ -743,10 +747,15 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, const
 				FAIL(S_OUT_OVERFLOW, 0);
 			const uint8_t *src = r.gbase + pos;
 			uint8_t *dst = out + outp;
-			if (lane < (outp & 15u))
+			if (lane < (outp & 15u)) {
 				out[(outp & ~15u) + lane] = (uint8_t)carry;
-			for (uint32_t i = lane; i < ncopy; i += 32)
-				dst[i] = src[i];
+				if (mir) mir[(outp & ~15u) + lane] = (uint8_t)carry;
+			}
+			for (uint32_t i = lane; i < ncopy; i += 32) {
+				const uint8_t v8 = src[i];
+				dst[i] = v8;
+				if (mir) mir[outp + i] = v8;
+			}
 			__syncwarp();
 			outp += ncopy;
 			if (lane < (outp & 15u))
@@ -854,7 +863,7 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, const
 		if (scratch) {
 			uint64_t P = (uint64_t)b.rd * 8 - (uint64_t)(int64_t)b.cnt;   /* bits from gbase */
 			uint32_t det = 0;
-			int st = lp_block(sm, r.gbase, r.glimit, (uint64_t)b.rd_end * 8, P, scratch, out, cap,
+			int st = lp_block(sm, r.gbase, r.glimit, (uint64_t)b.rd_end * 8, P, scratch, out, mir, cap,
 			    outp, carry, det);
 			bits_seek(sm, r, b, (uint32_t)(P >> 3));
 			bits_drop(b, (uint32_t)P & 7u);
@@ -873,7 +882,7 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, const
 			else
 				stop = decode_batch<true>(sm, r, b, my, n, stop_detail);
 
-			resolve_batch(sm, out, cap, outp, carry, my, n, stop, stop_detail);
+			resolve_batch(sm, out, mir, cap, outp, carry, my, n, stop, stop_detail);
 			if (stop == 1)
 				break;
 			if (stop < 0)
@@ -883,8 +892,10 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, const
 done:
 	/* the carry joins the rest of the output (error paths included: whatever was
 	 * produced is in global memory when the warp reports out_bytes) */
-	if (lane < (outp & 15u))
+	if (lane < (outp & 15u)) {
 		out[(outp & ~15u) + lane] = (uint8_t)carry;
+		if (mir) mir[(outp & ~15u) + lane] = (uint8_t)carry;
+	}
 	__syncwarp();
 	/* no bulk copy may still be in flight into this warp's ring when the
 	 * shared memory is handed to the next stream or the CTA exits */

@@ -168,7 +168,7 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
  *  <0  a B2I status (detail in `detail`); P / outp say how far decoding got
  */
 B2I_DEV int lp_block(WarpSmem *sm, const uint8_t *gbase, uint64_t glimit, uint64_t end_bits,
-    uint64_t &P, uint32_t *scratch, uint8_t *out, uint32_t cap, uint32_t &outp, uint32_t &carry,
+    uint64_t &P, uint32_t *scratch, uint8_t *out, uint8_t *mir, uint32_t cap, uint32_t &outp, uint32_t &carry,
     uint32_t &detail)
 {
 	const unsigned lane = b2i_lane();
@@ -229,7 +229,7 @@ B2I_DEV int lp_block(WarpSmem *sm, const uint8_t *gbase, uint64_t glimit, uint64
 				uint32_t avail = cnt - j < 32u ? cnt - j : 32u;
 				int32_t stop = 0;
 				/* resolve_batch takes as many symbols as its staging buffer holds */
-				uint32_t n = resolve_batch(sm, out, cap, outp, carry, my, avail, stop, detail);
+				uint32_t n = resolve_batch(sm, out, mir, cap, outp, carry, my, avail, stop, detail);
 				if (stop < 0) {
 					P = (uint64_t)wbase * 32u + mexit;
 					return stop;

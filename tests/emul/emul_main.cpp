@@ -51,7 +51,7 @@ static void *lane_main(void *p)
 	if (j->mode == 0) {
 		Ring ring;
 		ring_init(&j->sm, ring);
-		process_deflate_stream(&j->sm, ring, j->scratch, j->in, j->in_total, j->out, j->d, &j->res, g_crc_tab, g_xp8);
+		process_deflate_stream(&j->sm, ring, j->scratch, j->in, j->in_total, j->out, nullptr, j->d, &j->res, g_crc_tab, g_xp8);
 	} else {
 		crc_load_tables(j->sm.lit, g_crc_tab);
 		uint32_t raw0 = crc_warp_raw0(j->in + j->d.in_off, j->d.in_len, j->sm.lit, g_xp8);

@@ -200,3 +200,39 @@ def test_fuzz_garbage_and_mutations(ctx):
         names.append("hdr+garbage%d" % k)
     out = run_streams(ctx, streams, caps=[1 << 18] * len(streams), lead=2, gap=5)
     compare(names, *out)
+
+
+def test_pinned_host_buffers_take_the_mirrored_path(ctx):
+    """With pinned host buffers (b2i_host_alloc) b2i_decode_host lets the kernel
+    store the decoded bytes straight into host memory while it runs (no D2H pass)
+    and slices the batch over several streams: same bytes, same results."""
+    L = capi.lib()
+    parts = synth.split_text(600 * 65536, 65536, 91)
+    big = synth.synth_text(3 << 20, 92)
+    members = [synth.ZipMember("p%04d" % i, p) for i, p in enumerate(parts)]
+    members += [synth.ZipMember("big", big), synth.ZipMember("rnd", synth.synth_random(200000, 3)),
+                synth.ZipMember("fixed", big[:300000], strategy=zlib.Z_FIXED),
+                synth.ZipMember("bad", parts[0], crc=1)]
+    z = synth.make_zip(members)
+    from libarchive_b200 import reader
+    entries, _, _ = capi.zip_index(z)
+    descs, out_bytes, which = reader.plan_zip(entries)
+    n = len(descs)
+    h_in = L.b2i_host_alloc(len(z) + 64)
+    h_out = L.b2i_host_alloc(out_bytes + 64)
+    C.memmove(h_in, z, len(z))
+    C.memset(h_out, 0xEE, out_bytes + 64)
+    res = (capi.StreamResult * n)()
+    for _ in range(2):      # second call reuses the arena and the streams
+        ctx._check(L.b2i_decode_host(ctx.h, h_in, len(z), descs, n, h_out, out_bytes, res))
+    got = C.string_at(h_out, out_bytes + 64)
+    ores, oout = ob.decode_batch(z, descs, out_bytes)
+    for k in range(n):
+        assert (res[k].status, res[k].crc, res[k].out_bytes, res[k].in_bytes, res[k].flags) == \
+               (ores[k].status, ores[k].crc, ores[k].out_bytes, ores[k].in_bytes, ores[k].flags), k
+        o = descs[k].out_off
+        assert got[o:o + res[k].out_bytes] == oout[o:o + res[k].out_bytes], k
+    assert res[n - 1].flags & capi.R_CRC_MISMATCH
+    assert got[out_bytes:out_bytes + 64] == b"\xEE" * 64
+    L.b2i_host_free(h_in)
+    L.b2i_host_free(h_out)
