@@ -241,7 +241,7 @@ static size_t plan_block_bound(size_t n, size_t stored_bytes)
 
 /* mem_d / mem_h: caller-provided (arena) memory of mem_cap bytes, or NULL to allocate */
 static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cudaStream_t stream,
-    uint8_t *mem_d, uint8_t *mem_h, size_t mem_cap, b2i_plan **out)
+    cudaStream_t upload_stream, uint8_t *mem_d, uint8_t *mem_h, size_t mem_cap, b2i_plan **out)
 {
 	if (c == NULL || out == NULL || (n && descs == NULL) || n > 0x7fffffffu)
 		return fail(c, B2I_E_INVAL, "b2i_plan_create: bad arguments");
@@ -355,7 +355,7 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 	if (!work.empty()) memcpy(p->h_block + o_work, work.data(), work.size() * sizeof(B2iCrcWork));
 	if (!ents.empty()) memcpy(p->h_block + o_ents, ents.data(), ents.size() * sizeof(B2iCrcEntry));
 	if (!unsup.empty()) memcpy(p->h_block + o_unsup, unsup.data(), unsup.size() * 4);
-	cudaError_t e = cudaMemcpyAsync(p->d_block, p->h_block, upload_bytes, cudaMemcpyHostToDevice, stream);
+	cudaError_t e = cudaMemcpyAsync(p->d_block, p->h_block, upload_bytes, cudaMemcpyHostToDevice, upload_stream);
 	if (e != cudaSuccess) {
 		b2i_plan_destroy(p);
 		return fail(c, B2I_E_CUDA, "plan upload: %s", cudaGetErrorString(e));
@@ -368,7 +368,7 @@ extern "C" int b2i_plan_create(b2i_ctx *c, const b2i_stream_desc *descs, size_t 
 {
 	if (c == NULL)
 		return B2I_E_INVAL;
-	return b2i_plan_build(c, descs, n, c->stream, NULL, NULL, 0, out);
+	return b2i_plan_build(c, descs, n, c->stream, c->stream, NULL, NULL, 0, out);
 }
 
 extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, void *d_out, size_t out_bytes)
@@ -569,12 +569,12 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 	CU(c, cudaEventRecord(c->ev_free, c->stream));
 	CU(c, cudaStreamWaitEvent(c->s_in, c->ev_free, 0));
 
-	/* When host_out is pinned (device-accessible) the inflate kernel stores every
-	 * 16-byte unit to it as well, so decoded bytes cross the host link while the
-	 * kernel is still running instead of in a copy pass afterwards.  Stored
-	 * entries that want a copy keep the copy pass. */
+	/* Experimental (B2I_MIRROR=1): when host_out is pinned the inflate kernel can
+	 * store every 16-byte unit to it as well, so decoded bytes cross the host link
+	 * while the kernel runs.  Measured on B200: SM stores to system memory throttle
+	 * the kernel (22 GB/s end to end vs 31 GB/s with the copy pass), so it is off. */
 	uint8_t *mirror = NULL;
-	if (host_out != NULL && getenv("B2I_NO_MIRROR") == NULL) {
+	if (host_out != NULL && getenv("B2I_MIRROR") != NULL) {       /* opt-in: measured slower than the copy pass */
 		cudaPointerAttributes pa;
 		if (cudaPointerGetAttributes(&pa, host_out) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
 		    pa.devicePointer != NULL)
@@ -593,6 +593,13 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		cudaStream_t cs = c->s_cmp[s % B2I_PIPE_STREAMS];
 		if (sn == 0)
 			continue;
+		/* copy-in stream, in order: this slice's plan block, then its bytes.  (Copies
+		 * of one direction execute in submission order, so the small plan upload
+		 * must not queue behind later slices' data.) */
+		rc = b2i_plan_build(c, sd, sn, cs, c->s_in, c->arena_d + arena_off[s], c->arena_h + arena_off[s],
+		    align_up(plan_block_bound(sn, stored_bytes), 256), &plans[s]);
+		if (rc != B2I_OK)
+			break;
 		uint64_t lo = ~0ull, hi = 0;
 		for (size_t i = 0; i < sn; i++) {
 			if (sd[i].method != B2I_METHOD_DEFLATE && sd[i].method != B2I_METHOD_STORED)
@@ -610,21 +617,15 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		    cudaStreamWaitEvent(cs, c->ev_in[s], 0) != cudaSuccess) {
 			rc = fail(c, B2I_E_CUDA, "event"); break;
 		}
-		rc = b2i_plan_build(c, sd, sn, cs, c->arena_d + arena_off[s], c->arena_h + arena_off[s],
-		    align_up(plan_block_bound(sn, stored_bytes), 256), &plans[s]);
-		if (rc != B2I_OK)
-			break;
 		plans[s]->out_mirror = mirror;
 		rc = b2i_plan_launch(plans[s], c->d_in, in_bytes, c->d_out, out_bytes);
 		if (rc != B2I_OK)
 			break;
-		/* results of the slice ride on the compute stream right behind its kernels */
-		if (cudaMemcpyAsync(plans[s]->h_block + plans[s]->results_off, plans[s]->d_results,
-		    sn * sizeof(B2iResult), cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
-		    cudaEventRecord(c->ev_k[s], cs) != cudaSuccess ||
+		if (cudaEventRecord(c->ev_k[s], cs) != cudaSuccess ||
 		    cudaStreamWaitEvent(c->s_out, c->ev_k[s], 0) != cudaSuccess) {
 			rc = fail(c, B2I_E_CUDA, "event"); break;
 		}
+		/* copy-out stream, in order: the slice's decoded bytes, then its results */
 		if (host_out != NULL && mirror == NULL && plans[s]->max_out_end) {
 			uint64_t olo = ~0ull, ohi = 0;
 			for (size_t i = 0; i < sn; i++) {
@@ -639,6 +640,10 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 				    cudaMemcpyDeviceToHost, c->s_out);
 				if (e != cudaSuccess) { rc = fail(c, B2I_E_CUDA, "D2H: %s", cudaGetErrorString(e)); break; }
 			}
+		}
+		if (cudaMemcpyAsync(plans[s]->h_block + plans[s]->results_off, plans[s]->d_results,
+		    sn * sizeof(B2iResult), cudaMemcpyDeviceToHost, c->s_out) != cudaSuccess) {
+			rc = fail(c, B2I_E_CUDA, "results D2H"); break;
 		}
 	}
 	/* everything funnels into the copy-out stream (it waited on every slice's kernel) */

@@ -202,10 +202,10 @@ def test_fuzz_garbage_and_mutations(ctx):
     compare(names, *out)
 
 
-def test_pinned_host_buffers_take_the_mirrored_path(ctx):
-    """With pinned host buffers (b2i_host_alloc) b2i_decode_host lets the kernel
-    store the decoded bytes straight into host memory while it runs (no D2H pass)
-    and slices the batch over several streams: same bytes, same results."""
+def test_pinned_host_buffers_pipelined_path(ctx, monkeypatch):
+    """With pinned host buffers (b2i_host_alloc) b2i_decode_host pipelines slices over
+    three streams (and, with B2I_MIRROR=1, lets the kernel store straight to host memory)
+    - same bytes, same results either way."""
     L = capi.lib()
     parts = synth.split_text(600 * 65536, 65536, 91)
     big = synth.synth_text(3 << 20, 92)
@@ -223,16 +223,21 @@ def test_pinned_host_buffers_take_the_mirrored_path(ctx):
     C.memmove(h_in, z, len(z))
     C.memset(h_out, 0xEE, out_bytes + 64)
     res = (capi.StreamResult * n)()
-    for _ in range(2):      # second call reuses the arena and the streams
-        ctx._check(L.b2i_decode_host(ctx.h, h_in, len(z), descs, n, h_out, out_bytes, res))
-    got = C.string_at(h_out, out_bytes + 64)
     ores, oout = ob.decode_batch(z, descs, out_bytes)
-    for k in range(n):
-        assert (res[k].status, res[k].crc, res[k].out_bytes, res[k].in_bytes, res[k].flags) == \
-               (ores[k].status, ores[k].crc, ores[k].out_bytes, ores[k].in_bytes, ores[k].flags), k
-        o = descs[k].out_off
-        assert got[o:o + res[k].out_bytes] == oout[o:o + res[k].out_bytes], k
-    assert res[n - 1].flags & capi.R_CRC_MISMATCH
-    assert got[out_bytes:out_bytes + 64] == b"\xEE" * 64
+    for mirror in (False, True, False):      # later calls reuse the arena and the streams
+        if mirror:
+            monkeypatch.setenv("B2I_MIRROR", "1")
+        else:
+            monkeypatch.delenv("B2I_MIRROR", raising=False)
+        C.memset(h_out, 0xEE, out_bytes + 64)
+        ctx._check(L.b2i_decode_host(ctx.h, h_in, len(z), descs, n, h_out, out_bytes, res))
+        got = C.string_at(h_out, out_bytes + 64)
+        for k in range(n):
+            assert (res[k].status, res[k].crc, res[k].out_bytes, res[k].in_bytes, res[k].flags) == \
+                   (ores[k].status, ores[k].crc, ores[k].out_bytes, ores[k].in_bytes, ores[k].flags), k
+            o = descs[k].out_off
+            assert got[o:o + res[k].out_bytes] == oout[o:o + res[k].out_bytes], k
+        assert res[n - 1].flags & capi.R_CRC_MISMATCH
+        assert got[out_bytes:out_bytes + 64] == b"\xEE" * 64
     L.b2i_host_free(h_in)
     L.b2i_host_free(h_out)
