@@ -1,0 +1,407 @@
+/*
+ * archive_read_support_filter_gzip_b200.c — libarchive gzip read filter whose
+ * members are decoded on a B200 through include/b200inflate.h instead of zlib.
+ *
+ * Drop-in for libarchive/archive_read_support_filter_gzip.c: defines
+ * archive_read_support_filter_gzip (and the deprecated
+ * archive_read_support_compression_gzip, gzip.c:85-92) and registers a bidder
+ * with the unmodified read core (__archive_read_register_bidder,
+ * archive_read_private.h:242-245).  Written from scratch against that
+ * interface.
+ *
+ * The reference discovers members serially (header, zlib until Z_STREAM_END,
+ * 8-byte trailer, next header; gzip.c:431-511).  Here a window of upstream
+ * bytes is scanned for the BGZF member chain (BSIZE in the 'BC' extra
+ * subfield), every complete member of the window becomes a descriptor, ONE
+ * device pass decodes them all, and read() serves the decoded bytes in blocks
+ * of at most 64 KiB (gzip.c:314).  A member without BSIZE is decoded on the
+ * device from "here to the end of the window"; the number of bytes it consumed
+ * locates its trailer and the next header.  Trailer CRC-32 and ISIZE are
+ * verified (the reference leaves a TODO, gzip.c:423); set the environment
+ * variable B2I_GZIP_NO_VERIFY to get the reference's leniency.
+ */
+#include "archive_platform.h"
+
+#ifdef HAVE_ERRNO_H
+#include <errno.h>
+#endif
+#ifdef HAVE_STDLIB_H
+#include <stdlib.h>
+#endif
+#ifdef HAVE_STRING_H
+#include <string.h>
+#endif
+
+#include "archive.h"
+#include "archive_entry.h"
+#include "archive_private.h"
+#include "archive_read_private.h"
+
+#include "b200inflate.h"
+
+#define OUT_BLOCK      (64 * 1024)            /* gzip.c:314 */
+#define WINDOW_TARGET  ((size_t)256 << 20)    /* decode at most this much input per device pass */
+
+struct gz_b200 {
+	b2i_ctx        *ctx;
+	unsigned char  *out;          /* pinned: decoded bytes of the current window */
+	size_t          out_cap, out_len, served;
+	int             eof;          /* no more members */
+	int             failed;       /* sticky fatal */
+	int             verify;
+	uint32_t        mtime;
+	char           *name;
+	int             have_meta;
+};
+
+static int	gz_bid(struct archive_read_filter_bidder *, struct archive_read_filter *);
+static int	gz_init(struct archive_read_filter *);
+
+static const struct archive_read_filter_bidder_vtable gz_bidder_vtable = {
+	.bid = gz_bid,
+	.init = gz_init,
+};
+
+#if ARCHIVE_VERSION_NUMBER < 4000000
+int
+archive_read_support_compression_gzip(struct archive *a)
+{
+	return (archive_read_support_filter_gzip(a));
+}
+#endif
+
+int
+archive_read_support_filter_gzip(struct archive *_a)
+{
+	struct archive_read *a = (struct archive_read *)_a;
+
+	if (__archive_read_register_bidder(a, NULL, "gzip", &gz_bidder_vtable) != ARCHIVE_OK)
+		return (ARCHIVE_FATAL);
+	return (ARCHIVE_OK);
+}
+
+/* header parse over the upstream read-ahead buffer: returns the header length or 0
+ * (gzip.c:128-239 semantics, implemented by b2i_gzip_peek_header) */
+static size_t
+peek_header(struct archive_read_filter *up, b2i_gzip_member *m)
+{
+	ssize_t avail;
+	size_t want = 10;
+	const void *p;
+
+	for (;;) {
+		p = __archive_read_filter_ahead(up, want, &avail);
+		if (p == NULL) {
+			/* fewer than `want` bytes left: look at what there is */
+			p = __archive_read_filter_ahead(up, 1, &avail);
+			if (p == NULL || avail <= 0)
+				return (0);
+			return (b2i_gzip_peek_header(p, (size_t)avail, 0, m));
+		}
+		size_t hl = b2i_gzip_peek_header(p, (size_t)avail, 0, m);
+		if (hl != 0)
+			return (hl);
+		/* a header with long name/comment/extra may simply not fit yet */
+		if ((size_t)avail < want || want > (3u << 20))
+			return (0);
+		if (((const unsigned char *)p)[0] != 0x1f || ((const unsigned char *)p)[1] != 0x8b ||
+		    ((const unsigned char *)p)[2] != 8 || (((const unsigned char *)p)[3] & 0xE0))
+			return (0);
+		want = (size_t)avail >= want * 4 ? (size_t)avail + 1 : want * 4;
+	}
+}
+
+static int
+gz_bid(struct archive_read_filter_bidder *self, struct archive_read_filter *filter)
+{
+	(void)self;
+	return (peek_header(filter, NULL) ? 27 : 0);       /* 24 magic bits + 3 reserved-flag bits */
+}
+
+static int
+gz_read_header(struct archive_read_filter *self, struct archive_entry *entry)
+{
+	struct gz_b200 *g = (struct gz_b200 *)self->data;
+
+	if (g->mtime != 0)
+		archive_entry_set_mtime(entry, g->mtime, 0);
+	if (g->name)
+		archive_entry_set_pathname(entry, g->name);
+	return (ARCHIVE_OK);
+}
+
+static int
+fatal(struct archive_read_filter *self, struct gz_b200 *g, const char *msg)
+{
+	archive_set_error(&self->archive->archive, ARCHIVE_ERRNO_MISC, "%s", msg);
+	g->failed = 1;
+	return (ARCHIVE_FATAL);
+}
+
+static void
+note_header(struct gz_b200 *g, const unsigned char *base, const b2i_gzip_member *m)
+{
+	/* like the reference, the entry's name / mtime come from a member header */
+	g->mtime = m->mtime;
+	free(g->name);
+	g->name = m->name_offset ? strdup((const char *)base + m->name_offset) : NULL;
+	g->have_meta = 1;
+}
+
+/* decode the next window of members into g->out */
+static int
+next_window(struct archive_read_filter *self)
+{
+	struct gz_b200 *g = (struct gz_b200 *)self->data;
+	struct archive_read_filter *up = self->upstream;
+	const unsigned char *p;
+	ssize_t avail;
+	b2i_gzip_member *mem = NULL;
+	size_t n = 0, end = 0, i;
+
+	g->out_len = g->served = 0;
+	p = __archive_read_filter_ahead(up, 1, &avail);
+	if (p == NULL || avail <= 0) {
+		g->eof = 1;
+		return (ARCHIVE_OK);
+	}
+	/* ---- BGZF chain: every complete member in the read-ahead buffer ---- */
+	if (b2i_gzip_scan_bgzf(p, (size_t)avail, 0, &mem, &n, &end) != B2I_OK)
+		return (fatal(self, g, "Out of memory"));
+	if (n == 0) {
+		/* maybe the first member is only partly buffered: ask for all of it */
+		b2i_gzip_member m;
+		size_t hl = peek_header(up, &m);
+		b2i_free(mem);
+		mem = NULL;
+		if (hl == 0) {
+			g->eof = 1;           /* trailing garbage: silent end (gzip.c:450-454) */
+			return (ARCHIVE_OK);
+		}
+		p = __archive_read_filter_ahead(up, 1, &avail);
+		if (hl >= 18 && p != NULL) {
+			/* BSIZE known but the member ran past the buffer? */
+			const unsigned char *q = p;
+			if ((q[3] & 4) && q[12] == 'B' && q[13] == 'C') {
+				size_t total = (size_t)(q[16] | (q[17] << 8)) + 1;
+				const void *pp = __archive_read_filter_ahead(up, total, &avail);
+				if (pp == NULL)
+					return (fatal(self, g, "truncated gzip input"));
+				p = pp;
+				if (b2i_gzip_scan_bgzf(p, (size_t)avail, 0, &mem, &n, &end) != B2I_OK)
+					return (fatal(self, g, "Out of memory"));
+			}
+		}
+	}
+	if (g->ctx == NULL) {
+		int rc = b2i_ctx_create(0, NULL, &g->ctx);
+		if (rc != B2I_OK) {
+			b2i_free(mem);
+			return (fatal(self, g, "No usable B200 device; this build has no CPU inflate"));
+		}
+	}
+	if (n > 0) {
+		b2i_stream_desc *d = calloc(n, sizeof(*d));
+		b2i_stream_result *r = calloc(n, sizeof(*r));
+		size_t out = 0, in_used = 0, m_used = 0;
+		int rc;
+
+		if (d == NULL || r == NULL) {
+			free(d); free(r); b2i_free(mem);
+			return (fatal(self, g, "Can't allocate data for gzip decompression"));
+		}
+		for (i = 0; i < n; i++) {
+			if (i > 0 && mem[i].header_offset >= WINDOW_TARGET)
+				break;
+			d[i].in_off = mem[i].deflate_offset;
+			d[i].in_len = mem[i].deflate_len;
+			d[i].expect_out = mem[i].isize;
+			d[i].expect_crc = mem[i].crc32;
+			d[i].method = B2I_METHOD_DEFLATE;
+			d[i].flags = g->verify ? 0 : B2I_F_NO_CRC;
+			d[i].out_off = out;
+			d[i].out_cap = mem[i].isize;
+			out = (out + mem[i].isize + 15) & ~(size_t)15;
+			in_used = (size_t)(mem[i].deflate_offset + mem[i].deflate_len + 8);
+			m_used = i + 1;
+		}
+		if (!g->have_meta)
+			note_header(g, p, &mem[0]);
+		if (out + 16 > g->out_cap) {
+			b2i_host_free(g->out);
+			g->out_cap = out + 16 + (out >> 2);
+			if ((g->out = b2i_host_alloc(g->out_cap)) == NULL) {
+				g->out_cap = 0;
+				free(d); free(r); b2i_free(mem);
+				return (fatal(self, g, "Can't allocate data for gzip decompression"));
+			}
+		}
+		rc = b2i_decode_host(g->ctx, p, in_used, d, m_used, g->out, out, r);
+		if (rc != B2I_OK) {
+			free(d); free(r); b2i_free(mem);
+			return (fatal(self, g, b2i_last_error(g->ctx)));
+		}
+		/* members are served back to back: close the 16-byte alignment gaps */
+		size_t w = 0;
+		for (i = 0; i < m_used; i++) {
+			if (r[i].status != B2I_S_OK || (r[i].flags & B2I_R_IN_MISMATCH) ||
+			    (g->verify && (r[i].flags & (B2I_R_CRC_MISMATCH | B2I_R_OUT_MISMATCH)))) {
+				free(d); free(r); b2i_free(mem);
+				return (fatal(self, g, "gzip decompression failed"));
+			}
+			if (w != d[i].out_off)
+				memmove(g->out + w, g->out + d[i].out_off, (size_t)r[i].out_bytes);
+			w += (size_t)r[i].out_bytes;
+		}
+		g->out_len = w;
+		__archive_read_filter_consume(up, (int64_t)in_used);
+		free(d); free(r); b2i_free(mem);
+		return (ARCHIVE_OK);
+	}
+	b2i_free(mem);
+
+	/* ---- a member without BSIZE: decode to wherever its final block ends ---- */
+	{
+		b2i_gzip_member m;
+		b2i_stream_desc d;
+		b2i_stream_result r;
+		size_t hl = peek_header(up, &m), want;
+		size_t cap = 1 << 20;
+		int rc;
+
+		if (hl == 0) {
+			g->eof = 1;
+			return (ARCHIVE_OK);
+		}
+		p = __archive_read_filter_ahead(up, hl, &avail);
+		if (p == NULL)
+			return (fatal(self, g, "truncated gzip input"));
+		if (!g->have_meta)
+			note_header(g, p, &m);
+		want = (size_t)avail;
+		for (;;) {
+			/* grow the window until the stream ends inside it or upstream is exhausted */
+			const void *pp = __archive_read_filter_ahead(up, want, &avail);
+			int exhausted = 0;
+			if (pp == NULL) {
+				pp = __archive_read_filter_ahead(up, 1, &avail);
+				exhausted = 1;
+				if (pp == NULL || (size_t)avail <= hl)
+					return (fatal(self, g, "truncated gzip input"));
+			}
+			p = pp;
+			for (;;) {
+				memset(&d, 0, sizeof(d));
+				d.in_off = hl;
+				d.in_len = (size_t)avail - hl;
+				d.method = B2I_METHOD_DEFLATE;
+				d.flags = g->verify ? 0 : B2I_F_NO_CRC;
+				d.out_cap = cap;
+				if (cap + 16 > g->out_cap) {
+					b2i_host_free(g->out);
+					g->out_cap = cap + 16;
+					if ((g->out = b2i_host_alloc(g->out_cap)) == NULL) {
+						g->out_cap = 0;
+						return (fatal(self, g, "Can't allocate data for gzip decompression"));
+					}
+				}
+				rc = b2i_decode_host(g->ctx, p, (size_t)avail, &d, 1, g->out, cap, &r);
+				if (rc != B2I_OK)
+					return (fatal(self, g, b2i_last_error(g->ctx)));
+				if (r.status != B2I_S_OUT_OVERFLOW)
+					break;
+				cap *= 4;
+			}
+			if (r.status == B2I_S_BUF_ERROR && !exhausted && (size_t)avail >= want) {
+				want = (size_t)avail * 2;          /* the member continues past the window */
+				continue;
+			}
+			if (r.status == B2I_S_BUF_ERROR)
+				return (fatal(self, g, "truncated gzip input"));
+			if (r.status != B2I_S_OK)
+				return (fatal(self, g, "gzip decompression failed"));
+			break;
+		}
+		{
+			size_t trailer = hl + (size_t)r.in_bytes;
+			if ((size_t)avail < trailer + 8) {
+				const void *pp = __archive_read_filter_ahead(up, trailer + 8, &avail);
+				if (pp == NULL) {
+					g->failed = 1;      /* consume_trailer: fewer than 8 bytes (gzip.c:418-420) */
+					return (ARCHIVE_FATAL);
+				}
+				p = pp;
+			}
+			if (g->verify) {
+				uint32_t crc = (uint32_t)p[trailer] | (uint32_t)p[trailer + 1] << 8 |
+				    (uint32_t)p[trailer + 2] << 16 | (uint32_t)p[trailer + 3] << 24;
+				uint32_t isz = (uint32_t)p[trailer + 4] | (uint32_t)p[trailer + 5] << 8 |
+				    (uint32_t)p[trailer + 6] << 16 | (uint32_t)p[trailer + 7] << 24;
+				if (crc != r.crc || isz != (uint32_t)(r.out_bytes & 0xffffffffu))
+					return (fatal(self, g, "gzip decompression failed"));
+			}
+			g->out_len = (size_t)r.out_bytes;
+			__archive_read_filter_consume(up, (int64_t)(trailer + 8));
+		}
+	}
+	return (ARCHIVE_OK);
+}
+
+static ssize_t
+gz_read(struct archive_read_filter *self, const void **p)
+{
+	struct gz_b200 *g = (struct gz_b200 *)self->data;
+	size_t n;
+
+	if (g->failed)
+		return (ARCHIVE_FATAL);
+	/* an empty member (BGZF EOF marker) yields nothing: go on to the next window */
+	while (g->served == g->out_len && !g->eof) {
+		int r = next_window(self);
+		if (r != ARCHIVE_OK)
+			return (r);
+	}
+	n = g->out_len - g->served;
+	if (n > OUT_BLOCK)
+		n = OUT_BLOCK;
+	*p = n ? g->out + g->served : NULL;
+	g->served += n;
+	return ((ssize_t)n);
+}
+
+static int
+gz_close(struct archive_read_filter *self)
+{
+	struct gz_b200 *g = (struct gz_b200 *)self->data;
+
+	b2i_host_free(g->out);
+	b2i_ctx_destroy(g->ctx);
+	free(g->name);
+	free(g);
+	return (ARCHIVE_OK);
+}
+
+static const struct archive_read_filter_vtable gz_reader_vtable = {
+	.read = gz_read,
+	.close = gz_close,
+	.read_header = gz_read_header,
+};
+
+static int
+gz_init(struct archive_read_filter *self)
+{
+	struct gz_b200 *g;
+
+	self->code = ARCHIVE_FILTER_GZIP;
+	self->name = "gzip";
+	g = calloc(1, sizeof(*g));
+	if (g == NULL) {
+		archive_set_error(&self->archive->archive, ENOMEM,
+		    "Can't allocate data for gzip decompression");
+		return (ARCHIVE_FATAL);
+	}
+	g->verify = getenv("B2I_GZIP_NO_VERIFY") == NULL;
+	self->data = g;
+	self->vtable = &gz_reader_vtable;
+	return (ARCHIVE_OK);
+}
