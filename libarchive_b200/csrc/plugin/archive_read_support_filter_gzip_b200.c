@@ -148,7 +148,31 @@ note_header(struct gz_b200 *g, const unsigned char *base, const b2i_gzip_member 
 	g->have_meta = 1;
 }
 
-/* decode the next window of members into g->out */
+/* pending bytes move to the front; room for `need` more behind them */
+static int
+make_room(struct gz_b200 *g, size_t need)
+{
+	size_t pending = g->out_len - g->served;
+
+	if (pending + need + 16 > g->out_cap) {
+		size_t cap = pending + need + 16 + ((pending + need) >> 2);
+		unsigned char *nb = b2i_host_alloc(cap);
+		if (nb == NULL)
+			return (-1);
+		if (pending)
+			memcpy(nb, g->out + g->served, pending);
+		b2i_host_free(g->out);
+		g->out = nb;
+		g->out_cap = cap;
+	} else if (g->served && pending) {
+		memmove(g->out, g->out + g->served, pending);
+	}
+	g->served = 0;
+	g->out_len = pending;
+	return (0);
+}
+
+/* decode the next window of members and append the bytes to g->out */
 static int
 next_window(struct archive_read_filter *self)
 {
@@ -159,7 +183,6 @@ next_window(struct archive_read_filter *self)
 	b2i_gzip_member *mem = NULL;
 	size_t n = 0, end = 0, i;
 
-	g->out_len = g->served = 0;
 	p = __archive_read_filter_ahead(up, 1, &avail);
 	if (p == NULL || avail <= 0) {
 		g->eof = 1;
@@ -225,18 +248,13 @@ next_window(struct archive_read_filter *self)
 			in_used = (size_t)(mem[i].deflate_offset + mem[i].deflate_len + 8);
 			m_used = i + 1;
 		}
-		if (!g->have_meta)
-			note_header(g, p, &mem[0]);
-		if (out + 16 > g->out_cap) {
-			b2i_host_free(g->out);
-			g->out_cap = out + 16 + (out >> 2);
-			if ((g->out = b2i_host_alloc(g->out_cap)) == NULL) {
-				g->out_cap = 0;
-				free(d); free(r); b2i_free(mem);
-				return (fatal(self, g, "Can't allocate data for gzip decompression"));
-			}
+		note_header(g, p, &mem[m_used - 1]);
+		if (make_room(g, out) != 0) {
+			free(d); free(r); b2i_free(mem);
+			return (fatal(self, g, "Can't allocate data for gzip decompression"));
 		}
-		rc = b2i_decode_host(g->ctx, p, in_used, d, m_used, g->out, out, r);
+		unsigned char *dst = g->out + g->out_len;
+		rc = b2i_decode_host(g->ctx, p, in_used, d, m_used, dst, out, r);
 		if (rc != B2I_OK) {
 			free(d); free(r); b2i_free(mem);
 			return (fatal(self, g, b2i_last_error(g->ctx)));
@@ -250,10 +268,10 @@ next_window(struct archive_read_filter *self)
 				return (fatal(self, g, "gzip decompression failed"));
 			}
 			if (w != d[i].out_off)
-				memmove(g->out + w, g->out + d[i].out_off, (size_t)r[i].out_bytes);
+				memmove(dst + w, dst + d[i].out_off, (size_t)r[i].out_bytes);
 			w += (size_t)r[i].out_bytes;
 		}
-		g->out_len = w;
+		g->out_len += w;
 		__archive_read_filter_consume(up, (int64_t)in_used);
 		free(d); free(r); b2i_free(mem);
 		return (ARCHIVE_OK);
@@ -276,8 +294,7 @@ next_window(struct archive_read_filter *self)
 		p = __archive_read_filter_ahead(up, hl, &avail);
 		if (p == NULL)
 			return (fatal(self, g, "truncated gzip input"));
-		if (!g->have_meta)
-			note_header(g, p, &m);
+		note_header(g, p, &m);
 		want = (size_t)avail;
 		for (;;) {
 			/* grow the window until the stream ends inside it or upstream is exhausted */
@@ -297,15 +314,9 @@ next_window(struct archive_read_filter *self)
 				d.method = B2I_METHOD_DEFLATE;
 				d.flags = g->verify ? 0 : B2I_F_NO_CRC;
 				d.out_cap = cap;
-				if (cap + 16 > g->out_cap) {
-					b2i_host_free(g->out);
-					g->out_cap = cap + 16;
-					if ((g->out = b2i_host_alloc(g->out_cap)) == NULL) {
-						g->out_cap = 0;
-						return (fatal(self, g, "Can't allocate data for gzip decompression"));
-					}
-				}
-				rc = b2i_decode_host(g->ctx, p, (size_t)avail, &d, 1, g->out, cap, &r);
+				if (make_room(g, cap) != 0)
+					return (fatal(self, g, "Can't allocate data for gzip decompression"));
+				rc = b2i_decode_host(g->ctx, p, (size_t)avail, &d, 1, g->out + g->out_len, cap, &r);
 				if (rc != B2I_OK)
 					return (fatal(self, g, b2i_last_error(g->ctx)));
 				if (r.status != B2I_S_OUT_OVERFLOW)
@@ -340,7 +351,7 @@ next_window(struct archive_read_filter *self)
 				if (crc != r.crc || isz != (uint32_t)(r.out_bytes & 0xffffffffu))
 					return (fatal(self, g, "gzip decompression failed"));
 			}
-			g->out_len = (size_t)r.out_bytes;
+			g->out_len += (size_t)r.out_bytes;
 			__archive_read_filter_consume(up, (int64_t)(trailer + 8));
 		}
 	}
@@ -355,8 +366,9 @@ gz_read(struct archive_read_filter *self, const void **p)
 
 	if (g->failed)
 		return (ARCHIVE_FATAL);
-	/* an empty member (BGZF EOF marker) yields nothing: go on to the next window */
-	while (g->served == g->out_len && !g->eof) {
+	/* like the reference, fill a 64 KiB block across member boundaries: keep
+	 * decoding windows until that much is pending or the input ends */
+	while (g->out_len - g->served < OUT_BLOCK && !g->eof) {
 		int r = next_window(self);
 		if (r != ARCHIVE_OK)
 			return (r);
