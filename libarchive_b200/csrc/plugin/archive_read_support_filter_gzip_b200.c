@@ -48,6 +48,7 @@ struct gz_b200 {
 	size_t          out_cap, out_len, served;
 	int             eof;          /* no more members */
 	int             failed;       /* sticky fatal */
+	const char     *pending_fail; /* error to raise once the full blocks before it are served */
 	int             verify;
 	uint32_t        mtime;
 	char           *name;
@@ -262,10 +263,16 @@ next_window(struct archive_read_filter *self)
 		/* members are served back to back: close the 16-byte alignment gaps */
 		size_t w = 0;
 		for (i = 0; i < m_used; i++) {
-			if (r[i].status != B2I_S_OK || (r[i].flags & B2I_R_IN_MISMATCH) ||
-			    (g->verify && (r[i].flags & (B2I_R_CRC_MISMATCH | B2I_R_OUT_MISMATCH)))) {
-				free(d); free(r); b2i_free(mem);
-				return (fatal(self, g, "gzip decompression failed"));
+			int bad = r[i].status != B2I_S_OK || (r[i].flags & B2I_R_IN_MISMATCH) ||
+			    (g->verify && (r[i].flags & (B2I_R_CRC_MISMATCH | B2I_R_OUT_MISMATCH)));
+			if (bad) {
+				/* the reference has already handed out the full blocks before the bad
+				 * spot when zlib reports it; the partial block is dropped */
+				if (w != d[i].out_off)
+					memmove(dst + w, dst + d[i].out_off, (size_t)r[i].out_bytes);
+				w += (size_t)r[i].out_bytes;
+				g->pending_fail = "gzip decompression failed";
+				break;
 			}
 			if (w != d[i].out_off)
 				memmove(dst + w, dst + d[i].out_off, (size_t)r[i].out_bytes);
@@ -327,10 +334,12 @@ next_window(struct archive_read_filter *self)
 				want = (size_t)avail * 2;          /* the member continues past the window */
 				continue;
 			}
-			if (r.status == B2I_S_BUF_ERROR)
-				return (fatal(self, g, "truncated gzip input"));
-			if (r.status != B2I_S_OK)
-				return (fatal(self, g, "gzip decompression failed"));
+			if (r.status != B2I_S_OK) {
+				g->out_len += (size_t)r.out_bytes;
+				g->pending_fail = r.status == B2I_S_BUF_ERROR ? "truncated gzip input" :
+				    "gzip decompression failed";
+				return (ARCHIVE_OK);
+			}
 			break;
 		}
 		{
@@ -368,7 +377,7 @@ gz_read(struct archive_read_filter *self, const void **p)
 		return (ARCHIVE_FATAL);
 	/* like the reference, fill a 64 KiB block across member boundaries: keep
 	 * decoding windows until that much is pending or the input ends */
-	while (g->out_len - g->served < OUT_BLOCK && !g->eof) {
+	while (g->out_len - g->served < OUT_BLOCK && !g->eof && g->pending_fail == NULL) {
 		int r = next_window(self);
 		if (r != ARCHIVE_OK)
 			return (r);
@@ -376,6 +385,8 @@ gz_read(struct archive_read_filter *self, const void **p)
 	n = g->out_len - g->served;
 	if (n > OUT_BLOCK)
 		n = OUT_BLOCK;
+	if (n < OUT_BLOCK && g->pending_fail != NULL)
+		return (fatal(self, g, g->pending_fail));   /* the block the error fell into is not delivered */
 	*p = n ? g->out + g->served : NULL;
 	g->served += n;
 	return ((ssize_t)n);

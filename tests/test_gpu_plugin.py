@@ -123,5 +123,8 @@ def test_bgzf_and_plain_gzip_identical_reports():
         synth.gzip_member(b"", extra=b"XY\x02\x00zz")
     (ra, da), (rb, db) = both(f, raw=True)
     assert ra == rb and da == db == a + b
-    (ra, da), (rb, db) = both(f[:len(f) // 3], raw=True)
+    (ra, da), (rb, db) = both(f[:len(f) // 3], raw=True)          # truncated inside member 1
+    assert ra == rb and da == db
+    bad = bytearray(f); bad[len(f) // 4] ^= 0x40                      # corrupt member 1's deflate data
+    (ra, da), (rb, db) = both(bytes(bad), raw=True)
     assert [l.get("rd") for l in ra] == [l.get("rd") for l in rb] and [l.get("err") for l in ra] == [l.get("err") for l in rb]
