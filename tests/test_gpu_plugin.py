@@ -28,14 +28,15 @@ STREAMING_ONLY = {"test_read_format_zip_extra_padding.zip", "test_read_format_zi
 REFUSED = {"test_read_format_zip_encryption_data.zip"}       # different (still FAILED) message
 
 
-def run(binary, path, raw=False, opt=None):
+def run(binary, path, raw=False, opt=None, env=None):
     dump = path + ".dump." + os.path.basename(binary)
     cmd = [binary, "list", path, "--dump", dump]
     if raw:
         cmd.append("--raw")
     if opt:
         cmd += ["--opt", opt]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120,
+                       env=dict(os.environ, **env) if env else None)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.strip()]
     data = b""
@@ -71,7 +72,7 @@ def test_reference_fixture_through_the_dropin(name):
         assert hashlib.sha256(data).hexdigest() == exp["data_sha256"]
 
 
-def both(blob, raw=False, opt=None):
+def both(blob, raw=False, opt=None, env=None):
     need_dropin()
     if not ob.have_ref():
         pytest.skip("oracle/_ref not built")
@@ -79,7 +80,7 @@ def both(blob, raw=False, opt=None):
         f.write(blob)
     try:
         a = run(ob.REF_EXTRACT, f.name, raw, opt)
-        b = run(DROPIN, f.name, raw, opt)
+        b = run(DROPIN, f.name, raw, opt, env)
     finally:
         os.unlink(f.name)
     return a, b
@@ -126,5 +127,10 @@ def test_bgzf_and_plain_gzip_identical_reports():
     (ra, da), (rb, db) = both(f[:len(f) // 3], raw=True)          # truncated inside member 1
     assert ra == rb and da == db
     bad = bytearray(f); bad[len(f) // 4] ^= 0x40                      # corrupt member 1's deflate data
+    # the reference never checks the gzip trailer (gzip.c:423): with the same leniency the
+    # reports are identical; by default this build notices the CRC / ISIZE mismatch
+    (ra, da), (rb, db) = both(bytes(bad), raw=True, env={"B2I_GZIP_NO_VERIFY": "1"})
+    assert ra == rb and da == db
     (ra, da), (rb, db) = both(bytes(bad), raw=True)
-    assert [l.get("rd") for l in ra] == [l.get("rd") for l in rb] and [l.get("err") for l in ra] == [l.get("err") for l in rb]
+    if ra[0].get("rd") == 1:
+        assert rb[0].get("rd", rb[0].get("open")) == -30
