@@ -106,12 +106,29 @@ B2I_DEV uint32_t shf_r_wrap(uint32_t lo, uint32_t hi, uint32_t n)
 	return r;
 }
 B2I_DEV uint32_t byte2(uint32_t e) { return __byte_perm(e, 0, 0x4442); }
+/* v << s for s in 0..32 (0 when s == 32) */
+B2I_DEV uint32_t shl_clamp(uint32_t v, uint32_t s)
+{
+	uint32_t r;
+	asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+	return r;
+}
+/* the bits of v that a left shift by s (0..32) pushes past bit 31 */
+B2I_DEV uint32_t funnel_hi(uint32_t v, uint32_t s)
+{
+	uint32_t r;
+	asm("shf.l.clamp.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0), "r"(s));
+	return r;
+}
 #else
 B2I_DEV uint32_t shf_r_wrap(uint32_t lo, uint32_t hi, uint32_t n)
 {
 	return (uint32_t)((((uint64_t)hi << 32) | lo) >> (n & 31));
 }
 B2I_DEV uint32_t byte2(uint32_t e) { return (e >> 16) & 0xffu; }
+B2I_DEV uint32_t shl_clamp(uint32_t v, uint32_t s) { return s >= 32 ? 0 : v << s; }
+B2I_DEV uint32_t funnel_hi(uint32_t v, uint32_t s) { return s == 0 ? 0 : (s >= 32 ? v : v >> (32 - s)); }
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 #endif
 
 /* ------------------------------------------------------------------------ */
@@ -612,37 +629,34 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 	 * for round 2. */
 	for (uint32_t t0 = 0; t0 < T; t0 += 128) {
 		uint32_t v[4];
-		uint32_t di[4];
+		bool st[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			const uint32_t t = t0 + 32 * k + lane;
-			const uint32_t si = t < T ? c + t : c;          /* staging index */
+			const bool in = t < T;
+			const uint32_t si = c + (in ? t : 0);           /* staging index */
+			/* set bits at or below si in its bitmap word: shift them to the top and count */
 			const uint32_t own = (uint32_t)sm->wp[si >> 5] +
-			    (uint32_t)__popc(sm->bm[si >> 5] & (0xffffffffu >> (31u - (si & 31u)))) - 1u;
+			    (uint32_t)__popc(sm->bm[si >> 5] << (31u - (si & 31u))) - 1u;
 			const uint32_t opk = __shfl_sync(B2I_FULL, pk, own);
 			const uint32_t ro = __shfl_sync(B2I_FULL, rel, own);
 			const uint32_t olen = opk >> 16, oval = opk & 0xffffu;
-			di[k] = 0xffffffffu;
+			st[k] = in;
 			v[k] = oval;
-			if (t < T) {
-				if (olen == 1) {
-					di[k] = si;
-				} else {
-					uint32_t off = t - ro;
-					if (oval < olen)
-						off %= oval;           /* overlapping copy: period = distance */
-					int sidx = (int)(c + ro + off) - (int)oval;
-					if (sidx < 0) {
-						v[k] = g16[sidx];
-						di[k] = si;
-					}
-				}
+			if (in && olen != 1) {
+				uint32_t off = t - ro;
+				if (oval < olen)
+					off %= oval;               /* overlapping copy: period = distance */
+				int sidx = (int)(c + ro + off) - (int)oval;
+				st[k] = sidx < 0;
+				if (sidx < 0)
+					v[k] = g16[sidx];
 			}
 		}
 #pragma unroll
 		for (int k = 0; k < 4; k++)
-			if (di[k] != 0xffffffffu)
-				stg[di[k]] = (uint8_t)v[k];
+			if (st[k])
+				stg[c + t0 + 32 * k + lane] = (uint8_t)v[k];
 	}
 	__syncwarp();
 	/* round 2: bytes whose source is still in the staging buffer (the carry
@@ -666,11 +680,15 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 	/* flush whole 16-byte units, keep the rest as the new carry */
 	{
 		const uint32_t fill = c + T, groups = fill >> 4;
-		for (uint32_t g = lane; g < groups; g += 32) {
-			const uint4 v16 = *(const uint4 *)(stg + 16 * g);
-			*(uint4 *)(g16 + 16 * g) = v16;
-			if (mir)            /* host-mapped copy of the output: no separate D2H pass */
-				*(uint4 *)(mir + (outp - c) + 16 * g) = v16;
+		/* at most 44 units: two predicated stores, no loop */
+#pragma unroll
+		for (uint32_t g = lane; g < 64; g += 32) {
+			if (g < groups) {
+				const uint4 v16 = *(const uint4 *)(stg + 16 * g);
+				*(uint4 *)(g16 + 16 * g) = v16;
+				if (mir)            /* host-mapped copy of the output (B2I_MIRROR) */
+					*(uint4 *)(mir + (outp - c) + 16 * g) = v16;
+			}
 		}
 		if (lane < (fill & 15u))
 			carry = stg[16 * groups + lane];

@@ -72,12 +72,16 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 	uint32_t lo = 0, hi = 0, widx = start >> 5, ns = 0, tm = LT_NONE, ex = 0, nw = 0;
 	int32_t cnt = 0;
 	bool active = run;
+	const uint32_t stop_at = nominal_end <= hard_end ? nominal_end : hard_end + 1u;
 
-/* the word after the one being consumed is always already on its way (nw) */
-#define LP_FETCH(i_) gw[(wbase + (i_)) < max_word ? (wbase + (i_)) : max_word]
+/* the word after the one being consumed is always already on its way (nw);
+ * merging it in needs cnt <= 30: shift by cnt + 2 <= 32 */
+#define LP_FETCH(i_) gw[min(wbase + (i_), max_word)]
 #define LP_LOAD() do { \
-		uint64_t W_ = (((uint64_t)hi << 32) | lo) | ((uint64_t)nw << (cnt + 2)); \
-		lo = (uint32_t)W_; hi = (uint32_t)(W_ >> 32); cnt += 32; widx++; \
+		const uint32_t s_ = (uint32_t)cnt + 2u; \
+		lo |= shl_clamp(nw, s_); \
+		hi |= funnel_hi(nw, s_); \
+		cnt += 32; widx++; \
 		nw = LP_FETCH(widx); \
 	} while (0)
 #define LP_DROP(n_) do { \
@@ -134,19 +138,19 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 			LP_DROP(d);
 			token = (len << 16) | dist;
 		}
-		uint32_t pos = widx * 32u - (uint32_t)cnt;
-		if (pos > hard_end) {
-			tm = LT_EXH;
-			ex = pos;
-			active = false;
-			continue;
-		}
 		if (EMIT)
 			tok[ns] = token;
 		ns++;
-		if (pos >= nominal_end) {
+		/* one comparison per symbol: stop at the end of the segment or right
+		 * after the first symbol that runs past the end of the stream */
+		uint32_t pos = widx * 32u - (uint32_t)cnt;
+		if (pos >= stop_at) {
 			ex = pos;
 			active = false;
+			if (pos > hard_end) {
+				tm = LT_EXH;        /* that symbol does not count */
+				ns--;
+			}
 		}
 	}
 #undef LP_LOAD
