@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200inflate.so")
+LIB_PATH = os.environ.get("B2I_LIB") or os.path.join(_HERE, "libb200inflate.so")
 
 OK, E_INVAL, E_CUDA, E_NOMEM, E_NODEVICE, E_FORMAT = 0, -1, -2, -3, -4, -5
 S_OK, S_DATA_ERROR, S_BUF_ERROR, S_OUT_OVERFLOW, S_UNSUPPORTED = 0, -3, -5, -100, -101

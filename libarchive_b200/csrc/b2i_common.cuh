@@ -22,6 +22,18 @@ B2I_DEV unsigned b2i_lane() { unsigned l; asm volatile("mov.u32 %0, %%laneid;" :
 
 #define B2I_FULL 0xffffffffu
 
+/* -DB2I_DEBUG_BOUNDS: every staging / table / scratch / window index is checked and
+ * a violation traps the kernel (compute-sanitizer is not available on the pool;
+ * tests/test_gpu_inflate.py can be run against such a build via B2I_LIB) */
+#if defined(B2I_DEBUG_BOUNDS) && !defined(B2I_HOST_EMUL)
+#define B2I_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#elif defined(B2I_HOST_EMUL)
+#include <assert.h>
+#define B2I_CHECK(cond) assert(cond)
+#else
+#define B2I_CHECK(cond) do { } while (0)
+#endif
+
 /* must match include/b200inflate.h (static_asserts in b2i_api.cu) */
 struct B2iDesc {
 	uint64_t in_off, in_len, out_off, out_cap, expect_out;

@@ -458,8 +458,10 @@ B2I_DEV_NOINLINE int build_table(WarpSmem *sm, const uint8_t *lens, int nsyms, i
 				unsigned sbits = E_SUBBITS(sub), off = E_SUBOFF(sub);
 				unsigned low = code & ((1u << (L - root)) - 1u);
 				unsigned r = __brev(low) >> (32 - (L - root));
-				for (unsigned i = r; i < (1u << sbits); i += 1u << (L - root))
+				for (unsigned i = r; i < (1u << sbits); i += 1u << (L - root)) {
+					B2I_CHECK(off + i < (unsigned)cap);
 					table[off + i] = e;
+				}
 			}
 		}
 	}
@@ -475,6 +477,7 @@ B2I_DEV_NOINLINE int build_table(WarpSmem *sm, const uint8_t *lens, int nsyms, i
 B2I_DEV uint32_t lookup_sub(const uint32_t *table, const Bits &b, uint32_t e, int root)
 {
 	uint32_t idx = shf_r_wrap(b.lo, b.hi, root + 2) & ((1u << E_SUBBITS(e)) - 1u);
+	B2I_CHECK(E_SUBOFF(e) + idx < (root == LIT_ROOT ? LIT_TABLE : DIST_TABLE));
 	return table[E_SUBOFF(e) + idx];
 }
 
@@ -610,6 +613,7 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 	if (lane < c)
 		stg[lane] = (uint8_t)carry;
 	__syncwarp();
+	B2I_CHECK(c + T <= STAGE_BYTES);
 	if (len != 0)
 		atomicOr(&sm->bm[(c + rel) >> 5], 1u << ((c + rel) & 31u));
 	__syncwarp();
@@ -649,14 +653,17 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 					off %= oval;               /* overlapping copy: period = distance */
 				int sidx = (int)(c + ro + off) - (int)oval;
 				st[k] = sidx < 0;
+				B2I_CHECK(sidx >= -(int)(outp - c) && sidx < (int)STAGE_BYTES);
 				if (sidx < 0)
 					v[k] = g16[sidx];
 			}
 		}
 #pragma unroll
 		for (int k = 0; k < 4; k++)
-			if (st[k])
+			if (st[k]) {
+				B2I_CHECK(c + t0 + 32 * k + lane < STAGE_BYTES);
 				stg[c + t0 + 32 * k + lane] = (uint8_t)v[k];
+			}
 	}
 	__syncwarp();
 	/* round 2: bytes whose source is still in the staging buffer (the carry
@@ -672,6 +679,7 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 		for (uint32_t j = lane; j < mlen; j += 32) {
 			uint32_t off = mdist < mlen ? j % mdist : j;
 			int sidx = (int)(c + mrel + off) - (int)mdist;
+			B2I_CHECK(c + mrel + j < STAGE_BYTES && sidx < (int)(c + mrel + j));
 			if (sidx >= 0)
 				stg[c + mrel + j] = stg[sidx];
 		}

@@ -138,6 +138,7 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 			LP_DROP(d);
 			token = (len << 16) | dist;
 		}
+		B2I_CHECK(ns < LP_CAP);
 		if (EMIT)
 			tok[ns] = token;
 		ns++;
