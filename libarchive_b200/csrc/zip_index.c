@@ -55,8 +55,25 @@ err(char errbuf[128], const char *msg)
 /* MS-DOS date/time -> time_t, as libarchive/archive_time.c dos_to_unix does
  * (local time zone interpretation through mktime) */
 #include <time.h>
+static int64_t dos_time_slow(uint32_t d);
+
+/* mktime() costs microseconds and archives repeat time stamps: small
+ * direct-mapped memo (per call tree, no shared state) */
+struct dos_memo { uint32_t key[64]; int64_t val[64]; uint8_t set[64]; };
 static int64_t
-dos_time(uint32_t d)
+dos_time(struct dos_memo *m, uint32_t d)
+{
+	unsigned h = (d ^ (d >> 11) ^ (d >> 22)) & 63u;
+	if (!m->set[h] || m->key[h] != d) {
+		m->key[h] = d;
+		m->val[h] = dos_time_slow(d);
+		m->set[h] = 1;
+	}
+	return m->val[h];
+}
+
+static int64_t
+dos_time_slow(uint32_t d)
 {
 	struct tm ts;
 	uint16_t msTime = (uint16_t)(0xffff & d), msDate = (uint16_t)(d >> 16);
@@ -145,6 +162,9 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 	size_t tail, tail_start;
 	long i;
 	int found = 0;
+	struct dos_memo memo;
+
+	memset(&memo, 0, sizeof(memo));
 
 	if (out == NULL || (archive == NULL && size))
 		return B2I_E_INVAL;
@@ -249,7 +269,7 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 		if (r->flags & (ZIP_ENCRYPTED | ZIP_STRONG_ENCRYPTED))
 			out->has_encrypted_entries = 1;
 		r->method = (uint8_t)le16(p + 10);
-		r->mtime = dos_time(le32(p + 12));
+		r->mtime = dos_time(&memo, le32(p + 12));
 		r->crc = le32(p + 16);
 		r->csize = le32(p + 20);
 		r->usize = le32(p + 24);
@@ -319,7 +339,7 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 		}
 		uint64_t l_usize = le32(p + 22), l_csize = le32(p + 18);
 		uint32_t l_crc = le32(p + 14);
-		int64_t l_mtime = dos_time(le32(p + 10));
+		int64_t l_mtime = dos_time(&memo, le32(p + 10));
 		const char *why = NULL;
 
 		e->version = p[4];
