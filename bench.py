@@ -43,6 +43,7 @@ WORKLOADS = {
     "stored1m": "ZIP of 1024 x 1 MiB stored entries: CRC-32 verification only",
     "bgzf64k": "BGZF multi-member gzip, 64 KiB members (scaled: 16384 members = 1 GiB out)",
     "tiny4k": "ZIP64 of 4 KiB text entries (scaled: 65536 entries = 256 MiB)",
+    "mixed": "ZIP64, log-uniform entry sizes 1 KiB-16 MiB, dynamic/fixed/stored blocks mixed (scaled: 1 GiB out)",
 }
 
 
@@ -68,6 +69,8 @@ def build_workload(name, rank, scale=1.0):
         parts = synth.split_text(n * 4096, 4096, 5 + rank)
         return synth.make_zip([synth.ZipMember("t%06d" % i, p) for i, p in enumerate(parts)],
                               zip64=True, threads=threads), "zip"
+    if name == "mixed":
+        return synth.config4_zip64_mixed(total=max(8 << 20, int((1 << 30) * scale)), seed=4 + rank), "zip"
     raise SystemExit("unknown workload " + name)
 
 

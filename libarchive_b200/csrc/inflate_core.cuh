@@ -235,9 +235,13 @@ B2I_DEV void ring_wait(WarpSmem *sm, Ring &r, int h)
 /* make segment `seg` readable and keep the one after it in flight */
 B2I_DEV_NOINLINE void ring_ensure(WarpSmem *sm, Ring &r, uint32_t seg)
 {
-	if (seg >= r.next_issue) {
-		/* forward jump past everything requested: let in-flight copies land
-		 * (an mbarrier phase must complete before it is re-armed) */
+	if (seg >= r.next_issue || seg + 2 < r.next_issue) {
+		/* Not one of the two resident segments (next_issue-2, next_issue-1): a
+		 * forward jump past everything requested, or a step back of a few bytes
+		 * into a segment whose half has already been refilled (the bit reader
+		 * runs up to 8 bytes ahead of the byte position a stored block resumes
+		 * at).  Let in-flight copies land first: an mbarrier phase must complete
+		 * before it is re-armed. */
 		ring_wait(sm, r, 0);
 		ring_wait(sm, r, 1);
 		r.next_issue = seg;

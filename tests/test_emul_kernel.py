@@ -87,3 +87,15 @@ def test_reader_on_reference_gzip_fixtures(name):
 def test_reader_error_messages():
     gr.test_entry_errors_match_reference_messages(EmulContext())
     gr.test_ignorecrc32_option(EmulContext())
+
+
+def test_stored_block_resume_at_every_ring_phase():
+    """Regression (found on the GPU by the mixed-blocks config): after a stored block the
+    bit reader resumes at a byte position up to 8 bytes behind what it had loaded; when
+    that steps back across a 128-byte ring segment the half has already been refilled."""
+    txt = synth.synth_text(12000, 5)
+    rnd = synth.synth_random(3000, 6)
+    s = synth.deflate_mixed([(txt[:3000], 6, zlib.Z_DEFAULT_STRATEGY), (rnd[:1500], 6, zlib.Z_DEFAULT_STRATEGY),
+                             (txt[3000:4000], 1, zlib.Z_FIXED), (rnd[:60], 6, zlib.Z_DEFAULT_STRATEGY),
+                             (txt[4000:], 6, zlib.Z_DEFAULT_STRATEGY)])
+    check("mixed", s, cap=1 << 16, leads=range(0, 128))

@@ -241,3 +241,37 @@ def test_pinned_host_buffers_pipelined_path(ctx, monkeypatch):
         assert got[out_bytes:out_bytes + 64] == b"\xEE" * 64
     L.b2i_host_free(h_in)
     L.b2i_host_free(h_out)
+
+
+def test_block_type_changes_at_every_input_alignment(ctx):
+    """Streams that switch between dynamic, stored (incl. empty stored blocks from
+    Z_FULL_FLUSH) and fixed blocks, placed at all 128 phases of the 128-byte input
+    ring segments: resuming after a stored block may step back into a ring half that
+    has already been refilled (regression: found by the mixed-blocks config)."""
+    txt = synth.synth_text(60000, 5)
+    rnd = synth.synth_random(20000, 6)
+    s1 = synth.deflate_mixed([(txt[:7000], 6, zlib.Z_DEFAULT_STRATEGY), (rnd[:9000], 6, zlib.Z_DEFAULT_STRATEGY),
+                              (txt[7000:9000], 1, zlib.Z_FIXED), (rnd[:100], 6, zlib.Z_DEFAULT_STRATEGY),
+                              (txt[9000:40000], 6, zlib.Z_DEFAULT_STRATEGY)])
+    s2 = synth.deflate_raw(rnd, 6) + b""
+    streams, names = [], []
+    blob = bytearray()
+    items, out = [], 0
+    for phase in range(128):
+        for s in (s1, s2):
+            pad = (phase - len(blob)) % 128
+            blob += b"\x00" * pad
+            d = StreamDesc()
+            d.in_off, d.in_len, d.method = len(blob), len(s), 8
+            d.out_off, d.out_cap = out, 65536
+            out += 65536
+            blob += s
+            items.append(d); names.append("phase%d" % phase)
+    descs = capi.make_descs(items)
+    blob = bytes(blob)
+    inbuf = C.create_string_buffer(blob, len(blob) + 32)
+    outbuf = C.create_string_buffer(out + 32)
+    res = ctx.decode_host(inbuf, len(blob), descs, outbuf, out)
+    ores, oout = ob.decode_batch(blob, descs, out)
+    compare(names, descs, res, outbuf.raw, ores, oout)
+    assert all(r.status == 0 for r in res)
