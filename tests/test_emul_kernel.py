@@ -93,9 +93,9 @@ def test_stored_block_resume_at_every_ring_phase():
     """Regression (found on the GPU by the mixed-blocks config): after a stored block the
     bit reader resumes at a byte position up to 8 bytes behind what it had loaded; when
     that steps back across a 128-byte ring segment the half has already been refilled."""
-    txt = synth.synth_text(12000, 5)
-    rnd = synth.synth_random(3000, 6)
-    s = synth.deflate_mixed([(txt[:3000], 6, zlib.Z_DEFAULT_STRATEGY), (rnd[:1500], 6, zlib.Z_DEFAULT_STRATEGY),
-                             (txt[3000:4000], 1, zlib.Z_FIXED), (rnd[:60], 6, zlib.Z_DEFAULT_STRATEGY),
-                             (txt[4000:], 6, zlib.Z_DEFAULT_STRATEGY)])
-    check("mixed", s, cap=1 << 16, leads=range(0, 128))
+    txt = synth.synth_text(1500, 5)
+    rnd = synth.synth_random(300, 6)
+    s = synth.deflate_mixed([(txt[:600], 6, zlib.Z_DEFAULT_STRATEGY), (rnd[:250], 6, zlib.Z_DEFAULT_STRATEGY),
+                             (txt[600:800], 1, zlib.Z_FIXED), (rnd[:60], 6, zlib.Z_DEFAULT_STRATEGY),
+                             (txt[800:], 6, zlib.Z_DEFAULT_STRATEGY)])
+    check("mixed", s, cap=1 << 14, leads=range(0, 128))
