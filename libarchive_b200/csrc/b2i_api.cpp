@@ -28,7 +28,7 @@ static_assert(offsetof(b2i_stream_result, detail) == offsetof(B2iResult, detail)
 /* per-stream limits of this build: 32-bit positions inside one stream */
 #define B2I_MAX_STREAM_BYTES 0xFFFF0000ull
 #define B2I_PIPE_STREAMS 4
-#define B2I_PIPE_SLICES  8
+#define B2I_PIPE_SLICES  12
 
 struct b2i_ctx {
 	int device;
@@ -534,14 +534,32 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		    descs[i].in_off + descs[i].in_len > in_bytes)
 			return fail(c, B2I_E_INVAL, "a stream extends past the input buffer");
 	}
-	size_t K = (size_t)std::min<uint64_t>(B2I_PIPE_SLICES, std::max<uint64_t>(1, total_w / (32u << 20)));
-	if (const char *ek = getenv("B2I_PIPE_SLICES")) {        /* tuning knob */
-		int v = atoi(ek);
-		if (v >= 1 && v <= B2I_PIPE_SLICES)
-			K = (size_t)v;
+	/* Small first slices: their kernels run on an almost empty GPU and finish
+	 * early, so the copy-out stream (the longest stage) starts sooner; later
+	 * slices are large enough to keep the SMs full. */
+	static const double sched[] = { 1 / 32., 1 / 16., 1 / 8., 3 / 16., 1 / 4., 3 / 8., 1 / 2., 5 / 8.,
+		3 / 4., 7 / 8., 1. };
+	double frac[B2I_PIPE_SLICES];
+	size_t K = 1;
+	if (total_w >= ((uint64_t)64 << 20) && n >= 256) {
+		K = sizeof(sched) / sizeof(sched[0]);
+		for (size_t k = 0; k < K; k++)
+			frac[k] = sched[k];
+	} else {
+		K = (size_t)std::min<uint64_t>(8, std::max<uint64_t>(1, total_w / (32u << 20)));
+		if (n < 16 * K)
+			K = 1;
+		for (size_t k = 0; k < K; k++)
+			frac[k] = (double)(k + 1) / (double)K;
 	}
-	if (n < 16 * K)
-		K = 1;
+	if (const char *ek = getenv("B2I_PIPE_SLICES")) {        /* tuning knob: equal slices */
+		int v = atoi(ek);
+		if (v >= 1 && v <= B2I_PIPE_SLICES && n >= 16u * (size_t)v) {
+			K = (size_t)v;
+			for (size_t k = 0; k < K; k++)
+				frac[k] = (double)(k + 1) / (double)K;
+		}
+	}
 	size_t cut[B2I_PIPE_SLICES + 1];
 	{
 		uint64_t acc = 0;
@@ -549,7 +567,7 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		cut[0] = 0;
 		for (size_t i = 0; i < n && k < K; i++) {
 			acc += descs[i].in_len + descs[i].out_cap;
-			if (acc >= total_w * k / K)
+			while (k < K && (double)acc >= (double)total_w * frac[k - 1])
 				cut[k++] = i + 1;
 		}
 		while (k <= K)

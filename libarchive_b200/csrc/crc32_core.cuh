@@ -107,13 +107,21 @@ B2I_DEV uint32_t crc_warp_raw0(const uint8_t *p, uint64_t n, const uint32_t *tab
 	if (S) {
 		const uint4 *q = (const uint4 *)(p + (uint64_t)lane * S);
 		uint32_t s = 0;
-		for (uint64_t i = 0; i < S; i += 16) {
-			uint4 v = *q++;
+		/* two 16-byte loads in flight per lane: the next one is requested before
+		 * the current one is folded in */
+		uint4 v = *q++;
+		for (uint64_t i = 16; i < S; i += 16) {
+			const uint4 nv = *q++;
 			s = crc_word(s, v.x, tab);
 			s = crc_word(s, v.y, tab);
 			s = crc_word(s, v.z, tab);
 			s = crc_word(s, v.w, tab);
+			v = nv;
 		}
+		s = crc_word(s, v.x, tab);
+		s = crc_word(s, v.y, tab);
+		s = crc_word(s, v.z, tab);
+		s = crc_word(s, v.w, tab);
 		uint32_t Xall;
 		uint32_t body = crc_warp_merge(s, crc_xpow8(S, xp8), &Xall);
 		acc = crc_mulmod(acc, Xall) ^ body;

@@ -229,10 +229,14 @@ B2I_DEV int lp_block(WarpSmem *sm, const uint8_t *gbase, uint64_t glimit, uint64
 			const uint32_t cnt = __shfl_sync(B2I_FULL, o.nsym, rgn);
 			const uint32_t *rt = scratch + (uint32_t)rgn * LP_CAP;
 			uint32_t j = 0;
+			/* the tokens of the NEXT batch are requested before this one is resolved
+			 * (a batch almost always takes all 32; if it takes fewer, reload) */
+			uint32_t nxt = lane < cnt ? rt[lane] : 0;
 			while (j < cnt) {
-				uint32_t my = j + lane < cnt ? rt[j + lane] : 0;
-				uint32_t avail = cnt - j < 32u ? cnt - j : 32u;
+				const uint32_t my = nxt;
+				const uint32_t avail = cnt - j < 32u ? cnt - j : 32u;
 				int32_t stop = 0;
+				nxt = j + 32u + lane < cnt ? rt[j + 32u + lane] : 0;
 				/* resolve_batch takes as many symbols as its staging buffer holds */
 				uint32_t n = resolve_batch(sm, out, mir, cap, outp, carry, my, avail, stop, detail);
 				if (stop < 0) {
@@ -240,6 +244,8 @@ B2I_DEV int lp_block(WarpSmem *sm, const uint8_t *gbase, uint64_t glimit, uint64
 					return stop;
 				}
 				j += n;
+				if (n != 32u && j < cnt)
+					nxt = j + lane < cnt ? rt[j + lane] : 0;
 			}
 		}
 		P = (uint64_t)wbase * 32u + mexit;
