@@ -534,24 +534,14 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		    descs[i].in_off + descs[i].in_len > in_bytes)
 			return fail(c, B2I_E_INVAL, "a stream extends past the input buffer");
 	}
-	/* Small first slices: their kernels run on an almost empty GPU and finish
-	 * early, so the copy-out stream (the longest stage) starts sooner; later
-	 * slices are large enough to keep the SMs full. */
-	static const double sched[] = { 1 / 32., 1 / 16., 1 / 8., 3 / 16., 1 / 4., 3 / 8., 1 / 2., 5 / 8.,
-		3 / 4., 7 / 8., 1. };
+	/* Equal slices.  (A schedule with small first slices, meant to start the
+	 * copy-out stream earlier, measured slower: 37.5 vs 40.0 GB/s on config 1.) */
 	double frac[B2I_PIPE_SLICES];
-	size_t K = 1;
-	if (total_w >= ((uint64_t)64 << 20) && n >= 256) {
-		K = sizeof(sched) / sizeof(sched[0]);
-		for (size_t k = 0; k < K; k++)
-			frac[k] = sched[k];
-	} else {
-		K = (size_t)std::min<uint64_t>(8, std::max<uint64_t>(1, total_w / (32u << 20)));
-		if (n < 16 * K)
-			K = 1;
-		for (size_t k = 0; k < K; k++)
-			frac[k] = (double)(k + 1) / (double)K;
-	}
+	size_t K = (size_t)std::min<uint64_t>(8, std::max<uint64_t>(1, total_w / (32u << 20)));
+	if (n < 16 * K)
+		K = 1;
+	for (size_t k = 0; k < K; k++)
+		frac[k] = (double)(k + 1) / (double)K;
 	if (const char *ek = getenv("B2I_PIPE_SLICES")) {        /* tuning knob: equal slices */
 		int v = atoi(ek);
 		if (v >= 1 && v <= B2I_PIPE_SLICES && n >= 16u * (size_t)v) {
