@@ -48,6 +48,7 @@ struct b2i_ctx {
 	/* pipelined host path: copy-in / compute / copy-out streams, and a reusable
 	 * (grow-only) arena for the slice plans so that no call allocates */
 	cudaStream_t s_in, s_out, s_cmp[B2I_PIPE_STREAMS];
+	cudaStream_t s_team;     /* large streams (one CTA each) run beside the single-warp kernel */
 	cudaEvent_t ev_in[B2I_PIPE_SLICES], ev_k[B2I_PIPE_SLICES], ev_free;
 	bool pipe_ready;
 	uint8_t *arena_d; uint8_t *arena_h; size_t arena_cap;
@@ -57,7 +58,8 @@ struct b2i_ctx {
 struct b2i_plan {
 	b2i_ctx *ctx;
 	size_t n;
-	uint32_t n_deflate, n_stored, n_work, n_unsup;
+	uint32_t n_deflate, n_big, n_stored, n_work, n_unsup;   /* n_deflate: single-warp streams; n_big: team streams */
+	cudaEvent_t ev_fork, ev_join;                            /* team kernel runs beside the rest */
 	bool need_aligned_in;
 	uint64_t max_in_end, max_out_end;
 	/* device */
@@ -168,6 +170,7 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 	cudaFree(c->d_out);
 	cudaFree(c->arena_d);
 	cudaFreeHost(c->arena_h);
+	if (c->s_team) cudaStreamDestroy(c->s_team);
 	if (c->pipe_ready) {
 		cudaStreamDestroy(c->s_in);
 		cudaStreamDestroy(c->s_out);
@@ -299,6 +302,17 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 	std::stable_sort(deflate.begin(), deflate.end(), [&](uint32_t a, uint32_t b) {
 		return descs[a].in_len + descs[a].out_cap > descs[b].in_len + descs[b].out_cap;
 	});
+	/* streams with at least this much input get a whole CTA (inflate_team.cuh) */
+	uint64_t team_min = 256u << 10;
+	if (const char *ev = getenv("B2I_TEAM_MIN_BYTES"))
+		team_min = strtoull(ev, NULL, 10);
+	std::vector<uint32_t> big;
+	if (team_min != 0) {
+		std::vector<uint32_t> small;
+		for (uint32_t i : deflate)
+			(descs[i].in_len >= team_min ? big : small).push_back(i);
+		deflate.swap(small);
+	}
 
 	b2i_plan *p = new (std::nothrow) b2i_plan();
 	if (p == NULL)
@@ -307,10 +321,11 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 	p->ctx = c;
 	p->n = n;
 	p->n_deflate = (uint32_t)deflate.size();
+	p->n_big = (uint32_t)big.size();
 	p->n_stored = (uint32_t)ents.size();
 	p->n_work = (uint32_t)work.size();
 	p->n_unsup = (uint32_t)unsup.size();
-	p->need_aligned_in = !deflate.empty();
+	p->need_aligned_in = !deflate.empty() || !big.empty();
 	p->max_in_end = max_in;
 	p->max_out_end = max_out;
 	p->stream = stream;
@@ -318,13 +333,13 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 
 	size_t off = 0;
 	const size_t o_descs = off;   off = align_up(off + n * sizeof(B2iDesc), 256);
-	const size_t o_order = off;   off = align_up(off + deflate.size() * 4, 256);
+	const size_t o_order = off;   off = align_up(off + (deflate.size() + big.size()) * 4, 256);
 	const size_t o_work = off;    off = align_up(off + work.size() * sizeof(B2iCrcWork), 256);
 	const size_t o_ents = off;    off = align_up(off + ents.size() * sizeof(B2iCrcEntry), 256);
 	const size_t o_unsup = off;   off = align_up(off + unsup.size() * 4, 256);
 	const size_t upload_bytes = off;
 	const size_t o_partial = off; off = align_up(off + work.size() * 4, 256);
-	const size_t o_counter = off; off = align_up(off + 4, 256);
+	const size_t o_counter = off; off = align_up(off + 8, 256);
 	const size_t o_results = off; off = align_up(off + n * sizeof(B2iResult), 256);
 	p->block_bytes = off;
 	p->results_off = o_results;
@@ -350,8 +365,20 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 	p->d_counter = (unsigned int *)(p->d_block + o_counter);
 	p->d_results = (B2iResult *)(p->d_block + o_results);
 
+	if (!big.empty()) {
+		if (c->s_team == NULL && cudaStreamCreateWithFlags(&c->s_team, cudaStreamNonBlocking) != cudaSuccess) {
+			b2i_plan_destroy(p);
+			return fail(c, B2I_E_CUDA, "team stream");
+		}
+		if (cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+			b2i_plan_destroy(p);
+			return fail(c, B2I_E_CUDA, "team events");
+		}
+	}
 	if (n) memcpy(p->h_block + o_descs, descs, n * sizeof(B2iDesc));
 	if (!deflate.empty()) memcpy(p->h_block + o_order, deflate.data(), deflate.size() * 4);
+	if (!big.empty()) memcpy(p->h_block + o_order + deflate.size() * 4, big.data(), big.size() * 4);
 	if (!work.empty()) memcpy(p->h_block + o_work, work.data(), work.size() * sizeof(B2iCrcWork));
 	if (!ents.empty()) memcpy(p->h_block + o_ents, ents.data(), ents.size() * sizeof(B2iCrcEntry));
 	if (!unsup.empty()) memcpy(p->h_block + o_unsup, unsup.data(), unsup.size() * 4);
@@ -389,8 +416,20 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 	if (p->max_out_end && ((uintptr_t)d_out & 15))
 		return fail(c, B2I_E_INVAL, "d_out must be 16-byte aligned");
 	CU(c, cudaSetDevice(c->device));
+	if (p->n_big) {
+		/* fork: the team kernel (few, long CTAs) runs on its own stream next to everything else */
+		CU(c, cudaMemsetAsync(p->d_counter, 0, 8, p->stream));
+		CU(c, cudaEventRecord(p->ev_fork, p->stream));
+		CU(c, cudaStreamWaitEvent(c->s_team, p->ev_fork, 0));
+		CU(c, b2i_launch_inflate_team((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out, p->out_mirror, p->d_descs,
+		    p->d_results, p->d_order + p->n_deflate, p->n_big, p->d_counter + 1, c->d_crc_tab, c->d_xp8,
+		    c->d_scratch, c->d_slot_busy, c->num_sms, c->s_team));
+		CU(c, cudaEventRecord(p->ev_join, c->s_team));
+		c->launches++;
+	}
 	if (p->n_deflate) {
-		CU(c, cudaMemsetAsync(p->d_counter, 0, 4, p->stream));
+		if (!p->n_big)
+			CU(c, cudaMemsetAsync(p->d_counter, 0, 4, p->stream));
 		CU(c, b2i_launch_inflate((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out, p->out_mirror, p->d_descs,
 		    p->d_results, p->d_order, p->n_deflate, p->d_counter, c->d_crc_tab, c->d_xp8,
 		    getenv("B2I_UNIFORM_ONLY") ? NULL : c->d_scratch, c->d_slot_busy, c->num_sms, p->stream));
@@ -411,6 +450,8 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 		CU(c, b2i_launch_unsupported(p->d_descs, p->d_results, p->d_unsup, p->n_unsup, p->stream));
 		c->launches++;
 	}
+	if (p->n_big)
+		CU(c, cudaStreamWaitEvent(p->stream, p->ev_join, 0));      /* join */
 	return B2I_OK;
 }
 
@@ -438,6 +479,8 @@ extern "C" void b2i_plan_destroy(b2i_plan *p)
 		cudaFree(p->d_block);
 		cudaFreeHost(p->h_block);
 	}
+	if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+	if (p->ev_join) cudaEventDestroy(p->ev_join);
 	delete p;
 }
 

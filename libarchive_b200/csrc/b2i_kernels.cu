@@ -59,10 +59,66 @@ b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *_
 			break;
 		const uint32_t idx = order[slot];
 		const B2iDesc d = descs[idx];
-		process_deflate_stream(sm, ring, my_scratch, in, in_total, out, out_mirror, d, &results[idx], crc_tab, xp8);
+		process_deflate_stream(sm, ring, my_scratch, nullptr, in, in_total, out, out_mirror, d, &results[idx], crc_tab, xp8);
 		__syncwarp();
 	}
 	if (scratch && lane == 0) {
+		__threadfence();
+		atomicExch(&slot_busy[slot], 0u);
+	}
+}
+
+/*
+ * K1 for LARGE streams: one CTA (TEAM_WARPS warps) per stream, see inflate_team.cuh.
+ * Warp 0 pulls streams from the counter and owns them; the other warps serve its
+ * PASS / RESOLVE commands until it quits.
+ */
+extern "C" __global__ void __launch_bounds__(TEAM_LANES, 4)
+b2i_inflate_team_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *__restrict__ out,
+    uint8_t *__restrict__ out_mirror,
+    const B2iDesc *__restrict__ descs, B2iResult *__restrict__ results,
+    const uint32_t *__restrict__ order, uint32_t n, unsigned int *counter,
+    const uint32_t *__restrict__ crc_tab, const uint32_t *__restrict__ xp8, uint32_t *scratch,
+    unsigned int *slot_busy, uint32_t nslots)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	const unsigned w = threadIdx.x >> 5;
+	const unsigned lane = threadIdx.x & 31;
+	WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + w;
+	TeamShared *ts = reinterpret_cast<TeamShared *>(smem_raw + sizeof(WarpSmem) * TEAM_WARPS);
+	uint32_t slot = 0;
+
+	if (lane == 0) {
+		unsigned smid;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		slot = (smid * 56u + (blockIdx.x * TEAM_WARPS + w) % 56u) % nslots;
+		while (atomicCAS(&slot_busy[slot], 0u, 1u) != 0u)
+			slot = slot + 1 == nslots ? 0 : slot + 1;
+		ts->scratch[w] = scratch + (size_t)slot * LP_SCRATCH_WORDS;
+	}
+	slot = __shfl_sync(B2I_FULL, slot, 0);
+	__syncthreads();
+	if (w == 0) {
+		Ring ring;
+		ring_init(sm, ring);
+		for (;;) {
+			uint32_t s = 0;
+			if (lane == 0)
+				s = atomicAdd(counter, 1u);
+			s = __shfl_sync(B2I_FULL, s, 0);
+			if (s >= n)
+				break;
+			const uint32_t idx = order[s];
+			const B2iDesc d = descs[idx];
+			process_deflate_stream(sm, ring, ts->scratch[0], ts, in, in_total, out, out_mirror, d,
+			    &results[idx], crc_tab, xp8);
+			__syncwarp();
+		}
+		team_command(ts, TC_QUIT);
+	} else {
+		team_serve(ts, w, sm);
+	}
+	if (lane == 0) {
 		__threadfence();
 		atomicExch(&slot_busy[slot], 0u);
 	}
@@ -310,6 +366,26 @@ cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *ou
 	if (blocks > max_blocks)
 		blocks = max_blocks;
 	b2i_inflate_kernel<<<blocks, INFLATE_WARPS * 32, smem, st>>>(in, in_total, out, out_mirror, descs,
+	    results, order, n, counter, crc_tab, xp8, scratch, slot_busy, b2i_inflate_scratch_slots(num_sms));
+	return cudaGetLastError();
+}
+
+cudaError_t b2i_launch_inflate_team(const uint8_t *in, uint64_t in_total, uint8_t *out, uint8_t *out_mirror,
+    const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
+    unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
+    unsigned int *slot_busy, int num_sms, cudaStream_t st)
+{
+	static bool configured = false;
+	const size_t smem = sizeof(WarpSmem) * TEAM_WARPS + sizeof(TeamShared);
+	if (!configured) {
+		cudaError_t e = cudaFuncSetAttribute(b2i_inflate_team_kernel,
+		    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess)
+			return e;
+		configured = true;
+	}
+	uint32_t blocks = n < (uint32_t)num_sms * 2u ? n : (uint32_t)num_sms * 2u;
+	b2i_inflate_team_kernel<<<blocks, TEAM_LANES, smem, st>>>(in, in_total, out, out_mirror, descs,
 	    results, order, n, counter, crc_tab, xp8, scratch, slot_busy, b2i_inflate_scratch_slots(num_sms));
 	return cudaGetLastError();
 }

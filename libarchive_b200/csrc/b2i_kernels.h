@@ -27,6 +27,10 @@ cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *ou
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
     unsigned int *slot_busy, int num_sms, cudaStream_t st);
+cudaError_t b2i_launch_inflate_team(const uint8_t *in, uint64_t in_total, uint8_t *out, uint8_t *out_mirror,
+    const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
+    unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
+    unsigned int *slot_busy, int num_sms, cudaStream_t st);
 cudaError_t b2i_launch_crc_chunks(const uint8_t *in, uint8_t *out, const B2iDesc *descs,
     const B2iCrcWork *work, uint32_t nwork, uint32_t *partial, const uint32_t *crc_tab,
     const uint32_t *xp8, const uint32_t *ztab, const uint32_t *lane_mul, int num_sms, cudaStream_t st);

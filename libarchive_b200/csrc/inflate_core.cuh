@@ -566,8 +566,32 @@ B2I_DEV int decode_batch(WarpSmem *sm, Ring &r, Bits &b, uint32_t &my, uint32_t 
 #ifdef B2I_HOST_EMUL
 extern long g_stat_hist[64], g_stat_instage, g_stat_overlap, g_stat_batches, g_stat_bytes, g_stat_syms;
 #endif
-B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_t cap, uint32_t &outp, uint32_t &carry,
-    uint32_t my, uint32_t n, int32_t &stop, uint32_t &stop_detail)
+/*
+ * Several warps resolving consecutive token ranges of ONE stream at the same time
+ * (inflate_team.cuh).  Warp w owns output [range_start[w], range_end[w]); it may
+ * gather from an earlier warp's range only below that warp's published flush
+ * position, and the 16-byte unit it shares with its predecessor's tail is written
+ * bytewise (head_skip = bytes of that unit that are not ours).
+ */
+struct TeamLink {
+	volatile uint32_t *done_pos;      /* [nwarps] absolute output position flushed so far */
+	const uint32_t *range_start;      /* [nwarps] */
+	const uint32_t *range_end;        /* [nwarps] */
+	uint32_t w;                       /* this warp */
+	uint32_t head_skip;               /* leading foreign bytes of our first 16-byte unit */
+};
+
+#ifndef B2I_HOST_EMUL
+B2I_DEV uint8_t load_fresh(const uint8_t *p) { return __ldcg(p); }   /* L2: other warps' stores */
+B2I_DEV void fence_block() { __threadfence_block(); }
+#else
+B2I_DEV uint8_t load_fresh(const uint8_t *p) { return *(volatile const uint8_t *)p; }
+B2I_DEV void fence_block() { __sync_synchronize(); }
+#endif
+
+template <bool TEAM>
+B2I_DEV uint32_t resolve_batch_t(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_t cap, uint32_t &outp, uint32_t &carry,
+    uint32_t my, uint32_t n, int32_t &stop, uint32_t &stop_detail, TeamLink *tl)
 {
 	const unsigned lane = b2i_lane();
 	uint32_t len = lane < n ? my >> 16 : 0;
@@ -585,7 +609,7 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 	const uint32_t taken = n;
 	/* first symbol that cannot be written: bad distance or no room */
 	bool far = len >= 3 && val > outp + rel;
-	bool full = len != 0 && (rel + len > cap - outp);
+	bool full = len != 0 && (outp > cap || rel + len > cap - outp);
 	unsigned badmask = __ballot_sync(B2I_FULL, far || full);
 	if (badmask) {
 		int first = __ffs(badmask) - 1;
@@ -631,10 +655,35 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 			sm->wp[lane] = (uint8_t)(inc - pc);
 	}
 	__syncwarp();
+	if (TEAM) {
+		/* sources that lie in an earlier warp's range of this round must have been
+		 * flushed by that warp: wait for its published position */
+		const uint32_t own = tl->range_start[tl->w];
+		uint32_t hi = 0;
+		if (len >= 3) {
+			uint32_t send = outp + rel - val + (len < val ? len : val);   /* end of the source span */
+			hi = send < own ? send : own;
+			if (outp + rel - val >= own)
+				hi = 0;
+		}
+		for (int o = 16; o; o >>= 1) {
+			uint32_t t = __shfl_xor_sync(B2I_FULL, hi, o);
+			hi = t > hi ? t : hi;
+		}
+		for (uint32_t v = tl->w; v-- > 0;) {
+			uint32_t req = hi < tl->range_end[v] ? hi : tl->range_end[v];
+			if (req <= tl->range_start[v])
+				continue;
+			while (tl->done_pos[v] < req)
+				;
+		}
+		fence_block();
+	}
 	/* round 1, one output byte per lane: a literal is stored as is, a match byte
 	 * whose source was flushed to global memory before this batch is fetched
 	 * (four loads in flight per lane); sources inside the staging buffer wait
 	 * for round 2. */
+	const int hs = TEAM ? (int)tl->head_skip : 0;
 	for (uint32_t t0 = 0; t0 < T; t0 += 128) {
 		uint32_t v[4];
 		bool st[4];
@@ -656,10 +705,12 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 				if (oval < olen)
 					off %= oval;               /* overlapping copy: period = distance */
 				int sidx = (int)(c + ro + off) - (int)oval;
-				st[k] = sidx < 0;
+				/* team: the first hs bytes of the staging buffer stand for the previous
+				 * warp's tail, which lives in global memory, not here */
+				st[k] = sidx < hs;
 				B2I_CHECK(sidx >= -(int)(outp - c) && sidx < (int)STAGE_BYTES);
-				if (sidx < 0)
-					v[k] = g16[sidx];
+				if (sidx < hs)
+					v[k] = TEAM ? load_fresh(g16 + sidx) : g16[sidx];
 			}
 		}
 #pragma unroll
@@ -673,7 +724,7 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 	/* round 2: bytes whose source is still in the staging buffer (the carry
 	 * or this very batch), match by match in stream order */
 	unsigned mm = __ballot_sync(B2I_FULL,
-	    len >= 3 && c + rel + (len < val ? len : val) > val);
+	    len >= 3 && c + rel + (len < val ? len : val) > val + (uint32_t)hs);
 	while (mm) {
 		int src_lane = __ffs(mm) - 1;
 		mm &= mm - 1;
@@ -684,7 +735,7 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 			uint32_t off = mdist < mlen ? j % mdist : j;
 			int sidx = (int)(c + mrel + off) - (int)mdist;
 			B2I_CHECK(c + mrel + j < STAGE_BYTES && sidx < (int)(c + mrel + j));
-			if (sidx >= 0)
+			if (sidx >= hs)
 				stg[c + mrel + j] = stg[sidx];
 		}
 		__syncwarp();
@@ -697,20 +748,42 @@ B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_
 		for (uint32_t g = lane; g < 64; g += 32) {
 			if (g < groups) {
 				const uint4 v16 = *(const uint4 *)(stg + 16 * g);
-				*(uint4 *)(g16 + 16 * g) = v16;
-				if (mir)            /* host-mapped copy of the output (B2I_MIRROR) */
-					*(uint4 *)(mir + (outp - c) + 16 * g) = v16;
+				if (TEAM && g == 0 && tl->head_skip) {
+					/* shared with the previous warp's tail: only our bytes */
+					for (uint32_t i = tl->head_skip; i < 16; i++) {
+						g16[i] = stg[i];
+						if (mir) mir[(outp - c) + i] = stg[i];
+					}
+				} else {
+					*(uint4 *)(g16 + 16 * g) = v16;
+					if (mir)            /* host-mapped copy of the output (B2I_MIRROR) */
+						*(uint4 *)(mir + (outp - c) + 16 * g) = v16;
+				}
 			}
 		}
 		if (lane < (fill & 15u))
 			carry = stg[16 * groups + lane];
 		__syncwarp();
+		if (TEAM) {
+			if (groups)
+				tl->head_skip = 0;
+			fence_block();
+			if (lane == 0)
+				tl->done_pos[tl->w] = (outp - c) + 16 * groups;
+		}
 	}
 	outp += T;
 	return taken;
 }
 
+B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_t cap, uint32_t &outp, uint32_t &carry,
+    uint32_t my, uint32_t n, int32_t &stop, uint32_t &stop_detail)
+{
+	return resolve_batch_t<false>(sm, out, mir, cap, outp, carry, my, n, stop, stop_detail, nullptr);
+}
+
 #include "inflate_lp.cuh"
+#include "inflate_team.cuh"
 
 /* ------------------------------------------------------------------------ */
 /* one stream                                                               */
@@ -725,7 +798,7 @@ struct StreamOut {
 #define FAIL(st, dt) do { res.status = (st); res.detail = (dt); goto done; } while (0)
 #define NEEDOK() do { if (bits_exhausted(b)) FAIL(S_BUF_ERROR, 0); } while (0)
 
-B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, const uint8_t *in_base,
+B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, TeamShared *team, const uint8_t *in_base,
     uint64_t in_total, uint64_t in_off, uint64_t in_len, uint8_t *out, uint8_t *mir, uint64_t out_cap)
 {
 	const unsigned lane = b2i_lane();
@@ -893,8 +966,13 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, const
 		if (scratch) {
 			uint64_t P = (uint64_t)b.rd * 8 - (uint64_t)(int64_t)b.cnt;   /* bits from gbase */
 			uint32_t det = 0;
-			int st = lp_block(sm, r.gbase, r.glimit, (uint64_t)b.rd_end * 8, P, scratch, out, mir, cap,
-			    outp, carry, det);
+			int st = 2;
+			if (team)           /* a team of warps shares the rounds of a large stream */
+				st = lp_block_team(team, sm, r.gbase, r.glimit, (uint64_t)b.rd_end * 8, P, out, mir,
+				    cap, outp, carry, det);
+			if (st == 2)
+				st = lp_block(sm, r.gbase, r.glimit, (uint64_t)b.rd_end * 8, P, scratch, out, mir, cap,
+				    outp, carry, det);
 			bits_seek(sm, r, b, (uint32_t)(P >> 3));
 			bits_drop(b, (uint32_t)P & 7u);
 			if (st < 0)

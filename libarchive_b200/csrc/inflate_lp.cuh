@@ -55,6 +55,7 @@ struct LpOut {
 	uint32_t exit;     /* bit position (window relative) after the last symbol */
 	uint32_t nsym;
 	uint32_t term;     /* LT_* */
+	uint32_t nbytes;   /* output bytes of the nsym symbols (EMIT passes only) */
 };
 
 /*
@@ -69,7 +70,7 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 {
 	const char *litp = (const char *)sm->lit;
 	const char *distp = (const char *)sm->dist;
-	uint32_t lo = 0, hi = 0, widx = start >> 5, ns = 0, tm = LT_NONE, ex = 0, nw = 0;
+	uint32_t lo = 0, hi = 0, widx = start >> 5, ns = 0, tm = LT_NONE, ex = 0, nw = 0, nb = 0, lastb = 0;
 	int32_t cnt = 0;
 	bool active = run;
 	const uint32_t stop_at = nominal_end <= hard_end ? nominal_end : hard_end + 1u;
@@ -139,8 +140,11 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 			token = (len << 16) | dist;
 		}
 		B2I_CHECK(ns < LP_CAP);
-		if (EMIT)
+		if (EMIT) {
 			tok[ns] = token;
+			lastb = token >> 16;
+			nb += lastb;
+		}
 		ns++;
 		/* one comparison per symbol: stop at the end of the segment or right
 		 * after the first symbol that runs past the end of the stream */
@@ -151,6 +155,7 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 			if (pos > hard_end) {
 				tm = LT_EXH;        /* that symbol does not count */
 				ns--;
+				nb -= lastb;
 			}
 		}
 	}
@@ -161,6 +166,7 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 		o.exit = ex;
 		o.nsym = ns;
 		o.term = tm;
+		o.nbytes = nb;
 	}
 }
 
@@ -195,7 +201,7 @@ B2I_DEV int lp_block(WarpSmem *sm, const uint8_t *gbase, uint64_t glimit, uint64
 		const uint32_t nominal_end = p0 + (lane + 1u) * seg;
 		uint32_t start = p0 + lane * seg;
 		LpOut o;
-		o.exit = 0; o.nsym = 0; o.term = LT_NONE;
+		o.exit = 0; o.nsym = 0; o.term = LT_NONE; o.nbytes = 0;
 
 		/* pass A: where does every segment's decoder cross into the next one? */
 		lp_pass<false>(sm, gw, wbase, max_word, true, start, nominal_end, hard_end, tok, o);

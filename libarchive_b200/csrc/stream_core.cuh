@@ -11,11 +11,11 @@
 #pragma once
 #include "inflate_core.cuh"
 
-B2I_DEV void process_deflate_stream(WarpSmem *sm, Ring &ring, uint32_t *scratch, const uint8_t *in,
+B2I_DEV void process_deflate_stream(WarpSmem *sm, Ring &ring, uint32_t *scratch, TeamShared *team, const uint8_t *in,
     uint64_t in_total, uint8_t *out, uint8_t *out_mirror, const B2iDesc &d, B2iResult *res,
     const uint32_t *crc_tab_g, const uint32_t *xp8)
 {
-	StreamOut so = inflate_stream(sm, ring, scratch, in, in_total, d.in_off, d.in_len,
+	StreamOut so = inflate_stream(sm, ring, scratch, team, in, in_total, d.in_off, d.in_len,
 	    out + d.out_off, out_mirror ? out_mirror + d.out_off : nullptr, d.out_cap);
 	uint32_t crc = 0;
 

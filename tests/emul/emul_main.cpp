@@ -9,6 +9,7 @@
 
 thread_local unsigned tl_lane;
 thread_local EmulWarp *tl_warp;
+thread_local pthread_barrier_t *tl_team;
 
 static uint32_t g_crc_tab[1024];
 static uint32_t g_xp8[40];
@@ -51,7 +52,7 @@ static void *lane_main(void *p)
 	if (j->mode == 0) {
 		Ring ring;
 		ring_init(&j->sm, ring);
-		process_deflate_stream(&j->sm, ring, j->scratch, j->in, j->in_total, j->out, nullptr, j->d, &j->res, g_crc_tab, g_xp8);
+		process_deflate_stream(&j->sm, ring, j->scratch, nullptr, j->in, j->in_total, j->out, nullptr, j->d, &j->res, g_crc_tab, g_xp8);
 	} else {
 		crc_load_tables(j->sm.lit, g_crc_tab);
 		uint32_t raw0 = crc_warp_raw0(j->in + j->d.in_off, j->d.in_len, j->sm.lit, g_xp8);
@@ -100,4 +101,62 @@ extern "C" uint32_t emul_crc32(uint32_t crc, const uint8_t *buf, uint64_t off, u
 	uint32_t c = j->crc_out;
 	delete j;
 	return c;
+}
+
+
+/* ---- a team of TEAM_WARPS warps on one stream (inflate_team.cuh) ---------------- */
+struct TeamJob {
+	EmulWarp warp[TEAM_WARPS];
+	WarpSmem sm[TEAM_WARPS];
+	TeamShared ts;
+	pthread_barrier_t bar;
+	uint32_t *scratch[TEAM_WARPS];
+	const uint8_t *in; uint64_t in_total; uint8_t *out;
+	B2iDesc d; B2iResult res;
+};
+struct TeamLaneArg { TeamJob *job; unsigned w, lane; };
+
+static void *team_lane_main(void *p)
+{
+	TeamLaneArg *a = (TeamLaneArg *)p;
+	TeamJob *j = a->job;
+	tl_lane = a->lane;
+	tl_warp = &j->warp[a->w];
+	tl_team = &j->bar;
+	if (a->lane == 0)
+		j->ts.scratch[a->w] = j->scratch[a->w];
+	team_sync();
+	if (a->w == 0) {
+		Ring ring;
+		ring_init(&j->sm[0], ring);
+		process_deflate_stream(&j->sm[0], ring, j->scratch[0], &j->ts, j->in, j->in_total, j->out, nullptr,
+		    j->d, &j->res, g_crc_tab, g_xp8);
+		team_command(&j->ts, TC_QUIT);
+	} else {
+		team_serve(&j->ts, a->w, &j->sm[a->w]);
+	}
+	return NULL;
+}
+
+extern "C" int emul_inflate_team(const uint8_t *in, uint64_t in_total, uint8_t *out, const B2iDesc *d, B2iResult *res)
+{
+	if (!g_tab_ready) make_tables();
+	TeamJob *j = new TeamJob();
+	pthread_t th[TEAM_LANES];
+	TeamLaneArg args[TEAM_LANES];
+	j->in = in; j->in_total = in_total; j->out = out; j->d = *d;
+	pthread_barrier_init(&j->bar, NULL, TEAM_LANES);
+	for (unsigned w = 0; w < TEAM_WARPS; w++) {
+		pthread_barrier_init(&j->warp[w].bar, NULL, 32);
+		j->scratch[w] = (uint32_t *)malloc(LP_SCRATCH_WORDS * 4);
+	}
+	for (unsigned i = 0; i < TEAM_LANES; i++) {
+		args[i].job = j; args[i].w = i / 32; args[i].lane = i % 32;
+		pthread_create(&th[i], NULL, team_lane_main, &args[i]);
+	}
+	for (unsigned i = 0; i < TEAM_LANES; i++) pthread_join(th[i], NULL);
+	*res = j->res;
+	for (unsigned w = 0; w < TEAM_WARPS; w++) free(j->scratch[w]);
+	delete j;
+	return 0;
 }

@@ -25,6 +25,8 @@ struct EmulWarp {
 };
 extern thread_local unsigned tl_lane;
 extern thread_local EmulWarp *tl_warp;
+extern thread_local pthread_barrier_t *tl_team;     /* all lanes of all warps of a team */
+static inline void team_sync() { pthread_barrier_wait(tl_team); }
 
 static inline unsigned b2i_lane() { return tl_lane; }
 static inline void emul_sync() { pthread_barrier_wait(&tl_warp->bar); }
