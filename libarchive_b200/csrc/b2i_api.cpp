@@ -302,8 +302,12 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 	std::stable_sort(deflate.begin(), deflate.end(), [&](uint32_t a, uint32_t b) {
 		return descs[a].in_len + descs[a].out_cap > descs[b].in_len + descs[b].out_cap;
 	});
-	/* streams with at least this much input get a whole CTA (inflate_team.cuh) */
-	uint64_t team_min = 256u << 10;
+	/* Experimental, off by default (B2I_TEAM_MIN_BYTES=<bytes> turns it on): streams
+	 * with at least this much input get a whole CTA (inflate_team.cuh).  Measured on
+	 * B200 with 8 MiB streams: 1.15-1.18x only - decoding scales with the warps, but
+	 * resolving matches is a dependency chain through recent output, so the warps
+	 * of a team wait for each other. */
+	uint64_t team_min = 0;
 	if (const char *ev = getenv("B2I_TEAM_MIN_BYTES"))
 		team_min = strtoull(ev, NULL, 10);
 	std::vector<uint32_t> big;

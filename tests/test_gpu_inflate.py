@@ -275,3 +275,25 @@ def test_block_type_changes_at_every_input_alignment(ctx):
     ores, oout = ob.decode_batch(blob, descs, out)
     compare(names, descs, res, outbuf.raw, ores, oout)
     assert all(r.status == 0 for r in res)
+
+
+def test_team_decoder_opt_in(ctx, monkeypatch):
+    """B2I_TEAM_MIN_BYTES routes large streams to the experimental team kernel (one CTA
+    of four warps per stream): identical results, including errors and capacity limits."""
+    monkeypatch.setenv("B2I_TEAM_MIN_BYTES", "20000")
+    txt = synth.synth_text(3 << 20, 17)
+    rnd = synth.synth_random(300000, 18)
+    full = synth.deflate_raw(txt[:600000], 6)
+    flip = bytearray(full); flip[150000] ^= 0x20
+    streams = [synth.deflate_raw(txt, 6), synth.deflate_raw(txt[:900000], 9), full[:100000], bytes(flip), full,
+               synth.deflate_raw(txt[:700000], 1, zlib.Z_FIXED), synth.deflate_raw(rnd, 6),
+               synth.deflate_raw(bytes(2 << 20), 6) + b"", synth.deflate_raw(b"ab" * 400000 + txt[:100000], 6),
+               synth.deflate_mixed([(txt[:200000], 6, zlib.Z_DEFAULT_STRATEGY), (rnd[:90000], 6, zlib.Z_DEFAULT_STRATEGY),
+                                    (txt[200000:500000], 1, zlib.Z_FIXED)]),
+               synth.random_dynamic_stream(9, 40000), synth.deflate_raw(txt[:5000], 6)]
+    names = ["text3M", "text900k-l9", "truncated", "bitflip", "cap-too-small", "fixed", "stored", "zeros", "abab",
+             "mixed", "random-codes", "small"]
+    caps = [(3 << 20) + 64] * len(streams)
+    caps[4] = 250000
+    out = run_streams(ctx, streams, caps=caps, lead=5, gap=3)
+    compare(names, *out)
