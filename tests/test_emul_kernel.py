@@ -99,3 +99,28 @@ def test_stored_block_resume_at_every_ring_phase():
                              (txt[600:800], 1, zlib.Z_FIXED), (rnd[:60], 6, zlib.Z_DEFAULT_STRATEGY),
                              (txt[800:], 6, zlib.Z_DEFAULT_STRATEGY)])
     check("mixed", s, cap=1 << 14, leads=range(0, 128))
+
+
+def test_team_decoder_small_cases():
+    """inflate_team.cuh under the emulator (4 warps = 128 pthreads, slow: tiny inputs):
+    shared tables, 128-segment rounds, concurrent resolution with flush watermarks."""
+    txt = synth.synth_text(14000, 23)
+
+    def team(s, cap, lead):
+        buf = bytes(lead) + s
+        inb = C.create_string_buffer(buf + bytes(48), len(buf) + 48)
+        out = C.create_string_buffer(cap + 64)
+        d = StreamDesc()
+        d.in_off, d.in_len, d.out_cap, d.method = lead, len(s), cap, 8
+        r = StreamResult()
+        emu().emul_inflate_team(inb, len(buf), out, C.byref(d), C.byref(r))
+        return r, out.raw[:r.out_bytes]
+
+    full = synth.deflate_raw(txt, 6)
+    for name, s, cap in [("text", full, 1 << 15), ("truncated", full[:3000], 1 << 15), ("cap", full, 6000),
+                         ("fixed", synth.deflate_raw(txt[:7000], 6, zlib.Z_FIXED), 1 << 15)]:
+        o, od = ob.inflate(s, cap)
+        r, ed = team(s, cap, 9)
+        assert r.status == o.status and ed == od, (name, r.status, o.status)
+        if o.status == 0:
+            assert r.in_bytes == o.in_bytes and r.crc == (zlib.crc32(od) & 0xFFFFFFFF), name
