@@ -186,10 +186,17 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 extern "C" const char *b2i_last_error(const b2i_ctx *c) { return c ? c->err : "no context"; }
 extern "C" uint64_t b2i_ctx_launch_count(const b2i_ctx *c) { return c ? c->launches : 0; }
 
+#ifdef B2I_PHASE_CLOCKS
+void b2i_phase_dump(cudaStream_t st);
+#endif
+
 extern "C" int b2i_ctx_sync(b2i_ctx *c)
 {
 	if (c == NULL)
 		return B2I_E_INVAL;
+#ifdef B2I_PHASE_CLOCKS
+	b2i_phase_dump(c->stream);
+#endif
 	CU(c, cudaStreamSynchronize(c->stream));
 	return B2I_OK;
 }

@@ -73,3 +73,23 @@ struct B2iResult {
 #define R_OUT_MISMATCH 0x04
 
 #define CRC_POLY 0xEDB88320u
+
+/* -DB2I_PHASE_CLOCKS (make prof): per-phase cycle counters, summed over all warps,
+ * printed and cleared by b2i_ctx_sync.  Profiling builds only. */
+#if defined(B2I_PHASE_CLOCKS) && !defined(B2I_HOST_EMUL)
+static __device__ unsigned long long g_b2i_phase[8];
+#define PH_DECL()      long long ph_t_ = clock64()
+#define PH_ADD(slot)   do { long long n_ = clock64(); if (b2i_lane() == 0) atomicAdd(&g_b2i_phase[slot], (unsigned long long)(n_ - ph_t_)); ph_t_ = n_; } while (0)
+#define PH_COUNT(slot, v) do { if (b2i_lane() == 0) atomicAdd(&g_b2i_phase[slot], (unsigned long long)(v)); } while (0)
+#else
+#define PH_DECL()      do { } while (0)
+#define PH_ADD(slot)   do { } while (0)
+#define PH_COUNT(slot, v) do { } while (0)
+#endif
+#define PH_HEADER 0
+#define PH_LPDEC  1
+#define PH_LPRES  2
+#define PH_UNIF   3
+#define PH_CRC    4
+#define PH_BATCH  5   /* count of resolve batches in LP */
+#define PH_STORED 6

@@ -17,7 +17,19 @@
 #include "stream_core.cuh"
 #include "b2i_kernels.h"
 
+#include <stdio.h>
 #define INFLATE_WARPS 4
+
+#ifdef B2I_PHASE_CLOCKS
+__global__ void b2i_phase_dump_kernel()
+{
+	printf("B2I_PHASE header=%llu lpdec=%llu lpres=%llu unif=%llu crc=%llu batches=%llu stored=%llu\n",
+	    g_b2i_phase[0], g_b2i_phase[1], g_b2i_phase[2], g_b2i_phase[3], g_b2i_phase[4], g_b2i_phase[5],
+	    g_b2i_phase[6]);
+	for (int i = 0; i < 8; i++) g_b2i_phase[i] = 0;
+}
+void b2i_phase_dump(cudaStream_t st) { b2i_phase_dump_kernel<<<1, 1, 0, st>>>(); }
+#endif
 
 extern "C" __global__ void __launch_bounds__(INFLATE_WARPS * 32, 7)
 b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *__restrict__ out,

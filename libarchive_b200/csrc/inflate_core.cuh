@@ -820,6 +820,7 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, TeamS
 	r.next_issue = 0;
 	b.rd_end = lead + (uint32_t)in_len;
 	bits_seek(sm, r, b, lead);
+	PH_DECL();
 
 	do {
 		uint32_t hdr;
@@ -868,6 +869,7 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, TeamS
 				b.over = 1 << 20;  /* input ran out inside the block */
 				FAIL(S_BUF_ERROR, 0);
 			}
+			PH_ADD(PH_STORED);
 			continue;
 		}
 		if (hdr == 1) {
@@ -962,6 +964,7 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, TeamS
 				FAIL(S_DATA_ERROR, D_BAD_DIST_SET);
 		}
 
+		PH_ADD(PH_HEADER);
 		/* ---- symbols: lane-parallel while the block has enough input left ---- */
 		if (scratch) {
 			uint64_t P = (uint64_t)b.rd * 8 - (uint64_t)(int64_t)b.cnt;   /* bits from gbase */
@@ -975,6 +978,7 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, TeamS
 				    outp, carry, det);
 			bits_seek(sm, r, b, (uint32_t)(P >> 3));
 			bits_drop(b, (uint32_t)P & 7u);
+			PH_ADD(7);
 			if (st < 0)
 				FAIL(st, det);
 			if (st == 0)
@@ -996,6 +1000,7 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, TeamS
 			if (stop < 0)
 				FAIL(stop, stop_detail);
 		}
+		PH_ADD(PH_UNIF);
 	} while (!last);
 done:
 	/* the carry joins the rest of the output (error paths included: whatever was

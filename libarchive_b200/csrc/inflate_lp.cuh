@@ -202,6 +202,7 @@ B2I_DEV int lp_block(WarpSmem *sm, const uint8_t *gbase, uint64_t glimit, uint64
 		uint32_t start = p0 + lane * seg;
 		LpOut o;
 		o.exit = 0; o.nsym = 0; o.term = LT_NONE; o.nbytes = 0;
+		PH_DECL();
 
 		/* pass A: where does every segment's decoder cross into the next one? */
 		lp_pass<false>(sm, gw, wbase, max_word, true, start, nominal_end, hard_end, tok, o);
@@ -230,6 +231,7 @@ B2I_DEV int lp_block(WarpSmem *sm, const uint8_t *gbase, uint64_t glimit, uint64
 		const uint32_t mterm = __shfl_sync(B2I_FULL, o.term, m);
 		const uint32_t mexit = __shfl_sync(B2I_FULL, o.exit, m);
 		__syncwarp();
+		PH_ADD(PH_LPDEC);
 		/* tokens -> bytes, region after region in stream order */
 		for (int rgn = 0; rgn <= m; rgn++) {
 			const uint32_t cnt = __shfl_sync(B2I_FULL, o.nsym, rgn);
@@ -245,6 +247,7 @@ B2I_DEV int lp_block(WarpSmem *sm, const uint8_t *gbase, uint64_t glimit, uint64
 				nxt = j + 32u + lane < cnt ? rt[j + 32u + lane] : 0;
 				/* resolve_batch takes as many symbols as its staging buffer holds */
 				uint32_t n = resolve_batch(sm, out, mir, cap, outp, carry, my, avail, stop, detail);
+				PH_COUNT(PH_BATCH, 1);
 				if (stop < 0) {
 					P = (uint64_t)wbase * 32u + mexit;
 					return stop;
@@ -254,6 +257,7 @@ B2I_DEV int lp_block(WarpSmem *sm, const uint8_t *gbase, uint64_t glimit, uint64
 					nxt = j + lane < cnt ? rt[j + lane] : 0;
 			}
 		}
+		PH_ADD(PH_LPRES);
 		P = (uint64_t)wbase * 32u + mexit;
 		if (mterm == LT_EOB)
 			return 0;

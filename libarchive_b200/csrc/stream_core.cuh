@@ -19,6 +19,7 @@ B2I_DEV void process_deflate_stream(WarpSmem *sm, Ring &ring, uint32_t *scratch,
 	    out + d.out_off, out_mirror ? out_mirror + d.out_off : nullptr, d.out_cap);
 	uint32_t crc = 0;
 
+	PH_DECL();
 	if (so.status == S_OK && !(d.flags & F_NO_CRC)) {
 		/* the lit/len table is dead now: its space holds the slice tables */
 		crc_load_tables(sm->lit, crc_tab_g);
@@ -26,6 +27,7 @@ B2I_DEV void process_deflate_stream(WarpSmem *sm, Ring &ring, uint32_t *scratch,
 		crc = crc_finish(0, raw0, so.out_bytes, xp8);
 		__syncwarp();
 	}
+	PH_ADD(PH_CRC);
 	if (b2i_lane() == 0) {
 		uint32_t flags = 0;
 		if (so.status == S_OK) {

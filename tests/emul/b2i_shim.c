@@ -1,0 +1,40 @@
+/*
+ * b2i_shim.c — TEST INFRASTRUCTURE ONLY, never part of the product.
+ *
+ * Answers the part of the C ABI (include/b200inflate.h) that the libarchive
+ * plugin modules call with the CPU oracle (oracle/liboracle.so), so that the
+ * HOST logic of the plugins — header walking, block contract, error mapping,
+ * the state machine — can be run through the reference's own test programs in
+ * the no-GPU suite (tests/refsuite).  The product library libb200inflate.so
+ * has no such path: without a GPU b2i_ctx_create fails.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b200inflate.h"
+#include "oracle.h"
+
+struct b2i_ctx { int dummy; };
+
+int b2i_ctx_create(int device, void *cuda_stream, b2i_ctx **out)
+{
+	(void)device; (void)cuda_stream;
+	*out = calloc(1, sizeof(struct b2i_ctx));
+	return *out ? B2I_OK : B2I_E_NOMEM;
+}
+void b2i_ctx_destroy(b2i_ctx *c) { free(c); }
+const char *b2i_last_error(const b2i_ctx *c) { (void)c; return "shim"; }
+void *b2i_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void b2i_host_free(void *p) { free(p); }
+void b2i_free(void *p) { free(p); }
+
+int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes, const b2i_stream_desc *descs,
+    size_t n, void *host_out, size_t out_bytes, b2i_stream_result *results)
+{
+	(void)c;
+	_Static_assert(sizeof(orc_desc) == sizeof(b2i_stream_desc), "descriptor layouts differ");
+	_Static_assert(sizeof(orc_stream_result) == sizeof(b2i_stream_result), "result layouts differ");
+	return orc_decode_batch(host_in, in_bytes, (const orc_desc *)descs, n, host_out, out_bytes,
+	    (orc_stream_result *)results) == 0 ? B2I_OK : B2I_E_INVAL;
+}

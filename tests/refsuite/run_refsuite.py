@@ -1,0 +1,73 @@
+"""Run the reference's own libarchive_test programs (hot-path subset, built by
+tests/refsuite/Makefile from the unmodified reference sources) against the
+unmodified reference library and against the drop-in whose ZIP format and gzip
+filter modules run on the GPU; one process per test so that a crash is one
+result.  Prints / returns {test: (ref_status, dropin_status)}.
+
+Test infrastructure: compares, never ships."""
+from __future__ import annotations
+
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def list_tests(binary):
+    out = subprocess.run([binary, "-l"], capture_output=True, text=True, timeout=60).stdout
+    # "  0: test_name"
+    return [m.group(1) for m in re.finditer(r"^\s*\d+:\s+(\S+)", out, re.M)]
+
+
+def run_one(binary, test, timeout=300):
+    with tempfile.TemporaryDirectory() as tmp:
+        try:
+            p = subprocess.run([binary, "-r", os.path.join(REFDIR, "testdata"), "-q", test], cwd=tmp,
+                               capture_output=True, text=True, timeout=timeout,
+                               env=dict(os.environ, TMPDIR=tmp))
+        except subprocess.TimeoutExpired:
+            return "timeout", ""
+        text = p.stdout + p.stderr
+        for dp, _, fns in os.walk(tmp):       # the runner writes assertion details to <test>.log
+            for fn in fns:
+                if fn.endswith(".log"):
+                    text += open(os.path.join(dp, fn), errors="replace").read()[:6000]
+        if p.returncode < 0:
+            return f"signal{-p.returncode}", text[-8000:]
+        failed = re.search(r"Tests failed:\s+(\d+)", text)
+        skipped = re.search(r"Skips reported:\s+(\d+)", text)
+        asserts = re.search(r"Assertions failed:\s+(\d+)", text)
+        if p.returncode == 0 and (failed is None or failed.group(1) == "0"):
+            return ("skipped" if "skipped" in text.split("Totals:")[0].lower() and skipped and skipped.group(1) != "0"
+                    and re.search(r"Assertions checked:\s+0\b", text) else "ok"), ""
+        return f"FAIL({asserts.group(1) if asserts else '?'})", text[-8000:]
+
+
+def main(argv):
+    ref = os.path.join(REFDIR, "libarchive_test_ref")
+    drop = os.path.join(REFDIR, "libarchive_test_dropin")
+    only = argv[1:]
+    tests = [t for t in list_tests(ref) if not only or any(o in t for o in only)]
+    results, logs = {}, {}
+    for t in tests:
+        r, _ = run_one(ref, t)
+        d, log = run_one(drop, t)
+        results[t] = (r, d)
+        if d != r:
+            logs[t] = log
+        print(f"{t:64s} ref={r:10s} dropin={d}", flush=True)
+    same = sum(1 for r, d in results.values() if r == d)
+    print(f"== {same} of {len(results)} tests give the same verdict on both libraries")
+    return results, logs
+
+
+if __name__ == "__main__":
+    res, logs = main(sys.argv)
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    json.dump({"results": res, "logs": logs}, open(os.path.join(out, "refsuite.json"), "w"), indent=1)
