@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B2I_ABI_VERSION 1
+#define B2I_ABI_VERSION 2
 
 /* ---- return codes of the API functions -------------------------------- */
 #define B2I_OK            0
@@ -178,7 +178,12 @@ typedef struct b2i_zip_entry {
 	uint8_t  system;
 	uint32_t mode;                 /* as zip.c:3991-4006 derives it          */
 	uint32_t warn;                 /* B2I_ZW_* inconsistencies (WARN)        */
-	int64_t  mtime;
+	int64_t  mtime;                /* DOS time, then extras 0x5455 / 0x5855 (zip.c:597-650) */
+	int64_t  atime, ctime;         /* 0 when the archive carries none        */
+	uint32_t uid, gid;             /* extras 0x5855 / 0x7855 / 0x7875         */
+	uint64_t local_extra_offset;   /* the local header's extra field (for 0x7075) */
+	uint16_t local_extra_len;
+	uint16_t reserved[3];
 } b2i_zip_entry;
 
 #define B2I_ZW_CRC_INCONSISTENT   0x1

@@ -36,7 +36,9 @@ class ZipEntry(C.Structure):
                 ("crc32", C.c_uint32), ("name_offset", C.c_uint32), ("name_len", C.c_uint16),
                 ("zip_flags", C.c_uint16), ("method", C.c_uint16), ("version", C.c_uint8),
                 ("system", C.c_uint8), ("mode", C.c_uint32), ("warn", C.c_uint32),
-                ("mtime", C.c_int64)]
+                ("mtime", C.c_int64), ("atime", C.c_int64), ("ctime", C.c_int64),
+                ("uid", C.c_uint32), ("gid", C.c_uint32), ("local_extra_offset", C.c_uint64),
+                ("local_extra_len", C.c_uint16), ("reserved", C.c_uint16 * 3)]
 
 
 class ZipIndex(C.Structure):

@@ -16,9 +16,13 @@
  * device pass decodes them all, and read() serves the decoded bytes in blocks
  * of at most 64 KiB (gzip.c:314).  A member without BSIZE is decoded on the
  * device from "here to the end of the window"; the number of bytes it consumed
- * locates its trailer and the next header.  Trailer CRC-32 and ISIZE are
- * verified (the reference leaves a TODO, gzip.c:423); set the environment
- * variable B2I_GZIP_NO_VERIFY to get the reference's leniency.
+ * locates its trailer and the next header.  So that format bidding on a large
+ * member does not have to decode all of it, the FIRST block of such a member is
+ * produced from the bytes already buffered (decode with the output capped at
+ * one block); the member is decoded whole when more is asked for.  Like the
+ * reference, trailer CRC-32 and ISIZE are not checked by default (gzip.c:423
+ * leaves a TODO); the environment variable B2I_GZIP_VERIFY=1 turns the check on
+ * (mismatch => "gzip decompression failed").
  */
 #include "archive_platform.h"
 
@@ -38,6 +42,7 @@
 #include "archive_read_private.h"
 
 #include "b200inflate.h"
+#include <stdio.h>
 
 #define OUT_BLOCK      (64 * 1024)            /* gzip.c:314 */
 #define WINDOW_TARGET  ((size_t)256 << 20)    /* decode at most this much input per device pass */
@@ -50,6 +55,7 @@ struct gz_b200 {
 	int             failed;       /* sticky fatal */
 	const char     *pending_fail; /* error to raise once the full blocks before it are served */
 	int             verify;
+	size_t          member_skip;  /* bytes of the member at the read position already served */
 	uint32_t        mtime;
 	char           *name;
 	int             have_meta;
@@ -134,6 +140,7 @@ gz_read_header(struct archive_read_filter *self, struct archive_entry *entry)
 static int
 fatal(struct archive_read_filter *self, struct gz_b200 *g, const char *msg)
 {
+	if (getenv("B2I_GZ_TRACE")) fprintf(stderr, "gz fatal: %s (out_len %zu served %zu skip %zu)\n", msg, g->out_len, g->served, g->member_skip);
 	archive_set_error(&self->archive->archive, ARCHIVE_ERRNO_MISC, "%s", msg);
 	g->failed = 1;
 	return (ARCHIVE_FATAL);
@@ -285,14 +292,20 @@ next_window(struct archive_read_filter *self)
 	}
 	b2i_free(mem);
 
-	/* ---- a member without BSIZE: decode to wherever its final block ends ---- */
+	/* ---- a member without BSIZE ----
+	 * The decoder is given what is buffered and an output budget; the bytes it
+	 * consumed locate the trailer when the stream ends inside the budget.  The
+	 * budget starts at one block and quadruples every time more of the same member
+	 * is asked for (each pass decodes from the member's start and drops what was
+	 * already served), so looking at the head of a huge member is cheap, input is
+	 * only requested when the decoder really ran out of it, and the total work stays
+	 * within a small factor of one full decode. */
 	{
 		b2i_gzip_member m;
 		b2i_stream_desc d;
 		b2i_stream_result r;
-		size_t hl = peek_header(up, &m), want;
-		size_t cap = 1 << 20;
-		int rc;
+		size_t hl = peek_header(up, &m), want, budget, fresh, in_lim, in_use;
+		int rc, exhausted = 0;
 
 		if (hl == 0) {
 			g->eof = 1;
@@ -302,45 +315,68 @@ next_window(struct archive_read_filter *self)
 		if (p == NULL)
 			return (fatal(self, g, "truncated gzip input"));
 		note_header(g, p, &m);
+		{
+			/* a match is never written partially: one maximal match of slack fills the block */
+			size_t pending = g->out_len - g->served;
+			budget = g->member_skip ? g->member_skip * 4 :
+			    (pending < OUT_BLOCK ? OUT_BLOCK - pending : 1) + 258;
+		}
+		/* deflate expands by at most a few bytes per 64 KiB: this much input fills the
+		 * budget unless the stream idles in empty blocks (then the limit doubles) */
+		in_lim = hl + budget + (budget >> 8) + 4096;
 		want = (size_t)avail;
 		for (;;) {
-			/* grow the window until the stream ends inside it or upstream is exhausted */
-			const void *pp = __archive_read_filter_ahead(up, want, &avail);
-			int exhausted = 0;
-			if (pp == NULL) {
-				pp = __archive_read_filter_ahead(up, 1, &avail);
-				exhausted = 1;
-				if (pp == NULL || (size_t)avail <= hl)
-					return (fatal(self, g, "truncated gzip input"));
+			if ((size_t)avail <= hl || want > (size_t)avail) {
+				const void *pp = __archive_read_filter_ahead(up, want > hl ? want : hl + 1, &avail);
+				if (pp == NULL) {
+					pp = __archive_read_filter_ahead(up, 1, &avail);
+					exhausted = 1;
+					if (pp == NULL || (size_t)avail <= hl)
+						return (fatal(self, g, "truncated gzip input"));
+				}
+				p = pp;
 			}
-			p = pp;
-			for (;;) {
-				memset(&d, 0, sizeof(d));
-				d.in_off = hl;
-				d.in_len = (size_t)avail - hl;
-				d.method = B2I_METHOD_DEFLATE;
-				d.flags = g->verify ? 0 : B2I_F_NO_CRC;
-				d.out_cap = cap;
-				if (make_room(g, cap) != 0)
-					return (fatal(self, g, "Can't allocate data for gzip decompression"));
-				rc = b2i_decode_host(g->ctx, p, (size_t)avail, &d, 1, g->out + g->out_len, cap, &r);
-				if (rc != B2I_OK)
-					return (fatal(self, g, b2i_last_error(g->ctx)));
-				if (r.status != B2I_S_OUT_OVERFLOW)
-					break;
-				cap *= 4;
-			}
-			if (r.status == B2I_S_BUF_ERROR && !exhausted && (size_t)avail >= want) {
-				want = (size_t)avail * 2;          /* the member continues past the window */
+			memset(&d, 0, sizeof(d));
+			d.in_off = hl;
+			in_use = (size_t)avail < in_lim ? (size_t)avail : in_lim;
+			d.in_len = in_use - hl;
+			d.method = B2I_METHOD_DEFLATE;
+			d.flags = g->verify ? 0 : B2I_F_NO_CRC;
+			d.out_cap = budget;
+			if (make_room(g, budget) != 0)
+				return (fatal(self, g, "Can't allocate data for gzip decompression"));
+			rc = b2i_decode_host(g->ctx, p, in_use, &d, 1, g->out + g->out_len, budget, &r);
+			if (rc != B2I_OK)
+				return (fatal(self, g, b2i_last_error(g->ctx)));
+			if (r.status == B2I_S_BUF_ERROR && in_use < (size_t)avail) {
+				in_lim *= 2;                       /* more of what is buffered */
 				continue;
 			}
-			if (r.status != B2I_S_OK) {
-				g->out_len += (size_t)r.out_bytes;
-				g->pending_fail = r.status == B2I_S_BUF_ERROR ? "truncated gzip input" :
-				    "gzip decompression failed";
-				return (ARCHIVE_OK);
+			if (r.status == B2I_S_BUF_ERROR && !exhausted) {
+				want = (size_t)avail * 2;          /* the member continues past what is buffered */
+				in_lim *= 2;
+				continue;
+			}
+			if (r.status == B2I_S_OUT_OVERFLOW && r.out_bytes <= g->member_skip) {
+				budget *= 4;                       /* cannot happen with a growing budget; be safe */
+				continue;
 			}
 			break;
+		}
+		/* what earlier passes already served is not served twice */
+		fresh = (size_t)r.out_bytes > g->member_skip ? (size_t)r.out_bytes - g->member_skip : 0;
+		if (g->member_skip && fresh)
+			memmove(g->out + g->out_len, g->out + g->out_len + g->member_skip, fresh);
+		g->out_len += fresh;
+		if (r.status == B2I_S_OUT_OVERFLOW) {
+			g->member_skip = (size_t)r.out_bytes;  /* nothing consumed: the member stays at the read position */
+			return (ARCHIVE_OK);
+		}
+		g->member_skip = 0;
+		if (r.status != B2I_S_OK) {
+			g->pending_fail = r.status == B2I_S_BUF_ERROR ? "truncated gzip input" :
+			    "gzip decompression failed";
+			return (ARCHIVE_OK);
 		}
 		{
 			size_t trailer = hl + (size_t)r.in_bytes;
@@ -357,10 +393,11 @@ next_window(struct archive_read_filter *self)
 				    (uint32_t)p[trailer + 2] << 16 | (uint32_t)p[trailer + 3] << 24;
 				uint32_t isz = (uint32_t)p[trailer + 4] | (uint32_t)p[trailer + 5] << 8 |
 				    (uint32_t)p[trailer + 6] << 16 | (uint32_t)p[trailer + 7] << 24;
-				if (crc != r.crc || isz != (uint32_t)(r.out_bytes & 0xffffffffu))
-					return (fatal(self, g, "gzip decompression failed"));
+				if (crc != r.crc || isz != (uint32_t)(r.out_bytes & 0xffffffffu)) {
+					g->pending_fail = "gzip decompression failed";
+					return (ARCHIVE_OK);
+				}
 			}
-			g->out_len += (size_t)r.out_bytes;
 			__archive_read_filter_consume(up, (int64_t)(trailer + 8));
 		}
 	}
@@ -423,7 +460,7 @@ gz_init(struct archive_read_filter *self)
 		    "Can't allocate data for gzip decompression");
 		return (ARCHIVE_FATAL);
 	}
-	g->verify = getenv("B2I_GZIP_NO_VERIFY") == NULL;
+	g->verify = getenv("B2I_GZIP_VERIFY") != NULL;
 	self->data = g;
 	self->vtable = &gz_reader_vtable;
 	return (ARCHIVE_OK);

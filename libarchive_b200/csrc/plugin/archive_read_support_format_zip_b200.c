@@ -41,15 +41,10 @@
 #include "archive_string.h"
 
 #include "b200inflate.h"
-
-#define ZIP_ENCRYPTED            (1 << 0)
-#define ZIP_STRONG_ENCRYPTED     (1 << 6)
-#define ZIP_UTF8_NAME            (1 << 11)
-#define ZIP_CD_ENCRYPTED         (1 << 13)
-#define ZIP_BLOCK                (256 * 1024)      /* zip.c:2550 */
+#include "zip_b200_local.h"
 
 struct zip_b200 {
-	b2i_ctx            *ctx;
+	struct zb_common    c;             /* must be first */
 	b2i_zip_index       ix;
 	int                 have_index;
 	b2i_stream_desc    *descs;
@@ -65,29 +60,7 @@ struct zip_b200 {
 	size_t              cur;
 	int64_t             delivered;     /* entry_uncompressed_bytes_read */
 	int                 decoded, end_of_entry;
-	int                 ignore_crc32;
-	int                 has_encrypted_entries;
-	int                 init_default_conversion;
-	struct archive_string_conv *sconv, *sconv_default, *sconv_utf8;
-	struct archive_string format_name;
 };
-
-static const char *
-compression_name(int m)          /* the names zip.c:362-403 prints */
-{
-	static const struct { int id; const char *name; } t[] = {
-		{ 0, "uncompressed" }, { 1, "shrinking" }, { 2, "reduced-1" }, { 3, "reduced-2" },
-		{ 4, "reduced-3" }, { 5, "reduced-4" }, { 6, "imploded" }, { 7, "reserved" },
-		{ 8, "deflation" }, { 9, "deflation-64-bit" }, { 10, "ibm-terse" }, { 11, "reserved" },
-		{ 12, "bzip" }, { 13, "reserved" }, { 14, "lzma" }, { 15, "reserved" }, { 16, "reserved" },
-		{ 17, "reserved" }, { 18, "ibm-terse-new" }, { 19, "ibm-lz777" }, { 93, "zstd" },
-		{ 95, "xz" }, { 96, "jpeg" }, { 97, "wav-pack" }, { 98, "ppmd-1" }, { 99, "aes" }
-	};
-	for (size_t i = 0; i < sizeof(t) / sizeof(t[0]); i++)
-		if (t[i].id == m)
-			return (t[i].name);
-	return ("??");
-}
 
 /* ---- bid: is there a usable end-of-central-directory record? (zip.c:3720-3773) */
 static int
@@ -116,41 +89,13 @@ zip_b200_bid(struct archive_read *a, int best_bid)
 		return (0);
 	z->have_index = 1;
 	z->image_len = (size_t)size;
-	z->has_encrypted_entries = z->ix.has_encrypted_entries ? 1 :
-	    ARCHIVE_READ_FORMAT_ENCRYPTION_DONT_KNOW;
-	return (32);
+	return (32);            /* encrypted entries are reported as their headers are read (zip.c:962-972) */
 }
 
 static int
 zip_b200_options(struct archive_read *a, const char *key, const char *val)
-{                                                              /* zip.c:3271-3318 */
-	struct zip_b200 *z = (struct zip_b200 *)a->format->data;
-	int ret = ARCHIVE_FAILED;
-
-	if (strcmp(key, "compat-2x") == 0) {
-		z->init_default_conversion = (val != NULL) ? 1 : 0;
-		return (ARCHIVE_OK);
-	} else if (strcmp(key, "hdrcharset") == 0) {
-		if (val == NULL || val[0] == 0)
-			archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC,
-			    "zip: hdrcharset option needs a character-set name");
-		else {
-			z->sconv = archive_string_conversion_from_charset(&a->archive, val, 0);
-			if (z->sconv != NULL) {
-				if (strcmp(val, "UTF-8") == 0)
-					z->sconv_utf8 = z->sconv;
-				ret = ARCHIVE_OK;
-			} else
-				ret = ARCHIVE_FATAL;
-		}
-		return (ret);
-	} else if (strcmp(key, "ignorecrc32") == 0) {
-		z->ignore_crc32 = !(val == NULL || val[0] == 0);
-		return (ARCHIVE_OK);
-	} else if (strcmp(key, "mac-ext") == 0) {
-		return (ARCHIVE_OK);             /* resource-fork folding: not provided (off by default off macOS) */
-	}
-	return (ARCHIVE_WARN);
+{
+	return (zb_options(a, (struct zb_common *)a->format->data, key, val));
 }
 
 /* ---- the batch: one descriptor per decodable entry, one device pass ---------- */
@@ -177,7 +122,7 @@ zip_b200_decode_all(struct archive_read *a, struct zip_b200 *z)
 
 	if (z->decoded)
 		return (ARCHIVE_OK);
-	if (z->ctx == NULL && (rc = b2i_ctx_create(0, NULL, &z->ctx)) != B2I_OK) {
+	if (z->c.ctx == NULL && (rc = b2i_ctx_create(0, NULL, &z->c.ctx)) != B2I_OK) {
 		archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC,
 		    "No usable B200 device (b2i_ctx_create: %d); this build has no CPU inflate", rc);
 		return (ARCHIVE_FATAL);
@@ -203,7 +148,7 @@ zip_b200_decode_all(struct archive_read *a, struct zip_b200 *z)
 		d->expect_out = e->uncompressed_size;
 		d->expect_crc = e->crc32;
 		d->method = (uint8_t)e->method;
-		d->flags = z->ignore_crc32 ? B2I_F_NO_CRC : 0;
+		d->flags = z->c.ignore_crc32 ? B2I_F_NO_CRC : 0;
 		d->out_off = out;
 		if (e->method == 0) {
 			d->flags |= B2I_F_NO_COPY;          /* served from the archive image: zero copy */
@@ -220,10 +165,10 @@ zip_b200_decode_all(struct archive_read *a, struct zip_b200 *z)
 		archive_set_error(&a->archive, ENOMEM, "No memory for ZIP decompression");
 		return (ARCHIVE_FATAL);
 	}
-	if (n != 0 && (rc = b2i_decode_host(z->ctx, z->image, z->image_len, z->descs, n, z->out, out,
+	if (n != 0 && (rc = b2i_decode_host(z->c.ctx, z->image, z->image_len, z->descs, n, z->out, out,
 	    z->res)) != B2I_OK) {
 		archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC, "B200 decode failed (%d): %s", rc,
-		    b2i_last_error(z->ctx));
+		    b2i_last_error(z->c.ctx));
 		return (ARCHIVE_FATAL);
 	}
 	/* a stream that outgrows its directory size is decoded again, alone, with room,
@@ -238,7 +183,7 @@ zip_b200_decode_all(struct archive_read *a, struct zip_b200 *z)
 				break;
 			d.out_off = 0;
 			d.out_cap = cap;
-			if (b2i_decode_host(z->ctx, z->image, z->image_len, &d, 1, z->retry[i], cap,
+			if (b2i_decode_host(z->c.ctx, z->image, z->image_len, &d, 1, z->retry[i], cap,
 			    &z->res[i]) != B2I_OK)
 				break;
 		}
@@ -262,14 +207,18 @@ zip_b200_read_header(struct archive_read *a, struct archive_entry *entry)
 {
 	struct zip_b200 *z = (struct zip_b200 *)a->format->data;
 	const b2i_zip_entry *e;
-	struct archive_string_conv *sconv;
+	struct zb_meta m;
 	const char *name;
-	const wchar_t *wp;
-	int ret = ARCHIVE_OK;
+	int ret = ARCHIVE_OK, r;
 	unsigned mode;
 
-	if (z->has_encrypted_entries == ARCHIVE_READ_FORMAT_ENCRYPTION_DONT_KNOW)
-		z->has_encrypted_entries = 0;
+	if (z->c.has_encrypted_entries == ARCHIVE_READ_FORMAT_ENCRYPTION_DONT_KNOW)
+		z->c.has_encrypted_entries = 0;
+	/* the central directory is read on the first call; any encrypted record in it
+	 * makes the answer 1 from then on (zip.c:3963-3967) */
+	if (z->ix.has_encrypted_entries)
+		z->c.has_encrypted_entries = 1;
+	__archive_read_reset_passphrase(a);
 	a->archive.archive_format = ARCHIVE_FORMAT_ZIP;
 	if (a->archive.archive_format_name == NULL)
 		a->archive.archive_format_name = "ZIP";
@@ -298,7 +247,7 @@ zip_b200_read_header(struct archive_read *a, struct archive_entry *entry)
 		return (ARCHIVE_FATAL);
 	}
 	if (e->zip_flags & (ZIP_ENCRYPTED | ZIP_STRONG_ENCRYPTED)) {
-		z->has_encrypted_entries = 1;
+		z->c.has_encrypted_entries = 1;
 		archive_entry_set_is_data_encrypted(entry, 1);
 		if ((e->zip_flags & ZIP_CD_ENCRYPTED) && (e->zip_flags & ZIP_ENCRYPTED) &&
 		    (e->zip_flags & ZIP_STRONG_ENCRYPTED)) {
@@ -307,62 +256,30 @@ zip_b200_read_header(struct archive_read *a, struct archive_entry *entry)
 		}
 	}
 
-	/* pathname, with the reference's choice of conversion (zip.c:930-1003) */
-	if (z->sconv == NULL && !z->init_default_conversion) {
-		z->sconv_default = archive_string_default_conversion_for_read(&a->archive);
-		z->init_default_conversion = 1;
-	}
-	if (e->zip_flags & ZIP_UTF8_NAME) {
-		if (z->sconv_utf8 == NULL) {
-			z->sconv_utf8 = archive_string_conversion_from_charset(&a->archive, "UTF-8", 1);
-			if (z->sconv_utf8 == NULL)
-				return (ARCHIVE_FATAL);
-		}
-		sconv = z->sconv_utf8;
-	} else if (z->sconv != NULL)
-		sconv = z->sconv;
-	else
-		sconv = z->sconv_default;
+	/* pathname, the Unicode path of the local extra field, type fix-ups (zip.c:976-1103) */
+	memset(&m, 0, sizeof(m));
+	m.zip_flags = e->zip_flags;
+	m.system = e->system;
+	m.mode = e->mode;
+	m.mtime = e->mtime;
+	m.atime = e->atime;
+	m.ctime = e->ctime;
+	m.uid = e->uid;
+	m.gid = e->gid;
 	name = z->ix.names + e->name_offset;
-	if (archive_entry_copy_pathname_l(entry, name, e->name_len, sconv) != 0) {
-		if (errno == ENOMEM) {
-			archive_set_error(&a->archive, ENOMEM, "Can't allocate memory for Pathname");
-			return (ARCHIVE_FATAL);
-		}
-		archive_set_error(&a->archive, ARCHIVE_ERRNO_FILE_FORMAT,
-		    "Pathname cannot be converted from %s to current locale.",
-		    archive_string_conversion_charset_name(sconv));
-		ret = ARCHIVE_WARN;
+	r = zb_set_pathname(a, &z->c, entry, name, e->name_len, e->zip_flags);
+	if (r == ARCHIVE_FATAL)
+		return (r);
+	if (r != ARCHIVE_OK)
+		ret = r;
+	if (e->local_extra_len != 0 && e->local_extra_offset + e->local_extra_len <= z->image_len) {
+		struct zb_meta scratch = m;      /* everything but 0x7075 was applied by the index */
+		(void)zb_process_extra(a, &z->c, entry, z->image + e->local_extra_offset, e->local_extra_len,
+		    &scratch, NULL);
 	}
-	/* Windows archivers: backslash separators (zip.c:1015-1030) */
-	if (e->system == 0 && (wp = archive_entry_pathname_w(entry)) != NULL &&
-	    wcschr(wp, L'/') == NULL && wcschr(wp, L'\\') != NULL) {
-		size_t k, len = wcslen(wp);
-		wchar_t *w = malloc((len + 1) * sizeof(*w));
-		if (w != NULL) {
-			for (k = 0; k <= len; k++)
-				w[k] = wp[k] == L'\\' ? L'/' : wp[k];
-			archive_entry_copy_pathname_w(entry, w);
-			free(w);
-		}
-	}
-	mode = e->mode;
-	if ((mode & AE_IFMT) == AE_IFDIR) {
-		/* make sure directories end in '/' (zip.c:1064-1090) */
-		const char *cp = archive_entry_pathname(entry);
-		size_t len = cp ? strlen(cp) : 0;
-		if (len > 0 && cp[len - 1] != '/') {
-			char *s = malloc(len + 2);
-			if (s != NULL) {
-				memcpy(s, cp, len);
-				s[len] = '/';
-				s[len + 1] = 0;
-				archive_entry_set_pathname(entry, s);
-				free(s);
-			}
-		}
-	}
-	if (e->warn & B2I_ZW_CRC_INCONSISTENT && !z->ignore_crc32) {
+	zb_fix_path_and_mode(entry, &m);
+	mode = m.mode;
+	if (e->warn & B2I_ZW_CRC_INCONSISTENT && !z->c.ignore_crc32) {
 		archive_set_error(&a->archive, ARCHIVE_ERRNO_FILE_FORMAT, "Inconsistent CRC32 values");
 		ret = ARCHIVE_WARN;
 	}
@@ -376,8 +293,7 @@ zip_b200_read_header(struct archive_read *a, struct archive_entry *entry)
 		    "Inconsistent uncompressed size: central directory and local header disagree");
 		ret = ARCHIVE_WARN;
 	}
-	archive_entry_set_mode(entry, mode);
-	archive_entry_set_mtime(entry, e->mtime, 0);
+	zb_populate(entry, &m);
 
 	if ((mode & AE_IFMT) == AE_IFLNK) {
 		/* the link target is the entry body (zip.c:1160-1265) */
@@ -393,7 +309,7 @@ zip_b200_read_header(struct archive_read *a, struct archive_entry *entry)
 			if (e->method != 0 && e->method != 8) {
 				archive_set_error(&a->archive, ARCHIVE_ERRNO_FILE_FORMAT,
 				    "Unsupported ZIP compression method during decompression of link entry (%d: %s)",
-				    e->method, compression_name(e->method));
+				    e->method, zb_compression_name(e->method));
 				return (ARCHIVE_FAILED);
 			}
 			if (zip_b200_decode_all(a, z) != ARCHIVE_OK)
@@ -403,7 +319,7 @@ zip_b200_read_header(struct archive_read *a, struct archive_entry *entry)
 				if (r->status != B2I_S_OK) {
 					archive_set_error(&a->archive, ARCHIVE_ERRNO_FILE_FORMAT,
 					    "Unsupported ZIP compression method during decompression of link entry (%d: %s)",
-					    e->method, compression_name(e->method));
+					    e->method, zb_compression_name(e->method));
 					return (ARCHIVE_FAILED);
 				}
 				p = entry_bytes(z, z->cur);
@@ -414,21 +330,11 @@ zip_b200_read_header(struct archive_read *a, struct archive_entry *entry)
 			archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC, "Truncated Zip file");
 			return (ARCHIVE_FATAL);
 		}
-		sconv = z->sconv;
-		if (sconv == NULL && (e->zip_flags & ZIP_UTF8_NAME))
-			sconv = z->sconv_utf8;
-		if (sconv == NULL)
-			sconv = z->sconv_default;
-		if (archive_entry_copy_symlink_l(entry, (const char *)p, len, sconv) != 0) {
-			if (errno == ENOMEM) {
-				archive_set_error(&a->archive, ENOMEM, "Can't allocate memory for Symlink");
-				return (ARCHIVE_FATAL);
-			}
-			archive_set_error(&a->archive, ARCHIVE_ERRNO_FILE_FORMAT,
-			    "Symlink cannot be converted from %s to current locale.",
-			    archive_string_conversion_charset_name(sconv));
-			ret = ARCHIVE_WARN;
-		}
+		r = zb_set_symlink(a, &z->c, entry, p, len, e->zip_flags);
+		if (r == ARCHIVE_FATAL)
+			return (r);
+		if (r != ARCHIVE_OK)
+			ret = r;
 		z->end_of_entry = 1;
 	} else {
 		archive_entry_set_size(entry, (int64_t)e->uncompressed_size);
@@ -436,10 +342,10 @@ zip_b200_read_header(struct archive_read *a, struct archive_entry *entry)
 			z->end_of_entry = 1;                 /* no body: EOF immediately (zip.c:1275-1277) */
 	}
 
-	archive_string_empty(&z->format_name);
-	archive_string_sprintf(&z->format_name, "ZIP %d.%d (%s)", e->version / 10, e->version % 10,
-	    compression_name(e->method));
-	a->archive.archive_format_name = z->format_name.s;
+	archive_string_empty(&z->c.format_name);
+	archive_string_sprintf(&z->c.format_name, "ZIP %d.%d (%s)", e->version / 10, e->version % 10,
+	    zb_compression_name(e->method));
+	a->archive.archive_format_name = z->c.format_name.s;
 	return (ret);
 }
 
@@ -454,8 +360,8 @@ zip_b200_read_data(struct archive_read *a, const void **buff, size_t *size, int6
 	size_t n;
 	int last;
 
-	if (z->has_encrypted_entries == ARCHIVE_READ_FORMAT_ENCRYPTION_DONT_KNOW)
-		z->has_encrypted_entries = 0;
+	if (z->c.has_encrypted_entries == ARCHIVE_READ_FORMAT_ENCRYPTION_DONT_KNOW)
+		z->c.has_encrypted_entries = 0;
 	*offset = z->delivered;
 	*size = 0;
 	*buff = NULL;
@@ -464,14 +370,14 @@ zip_b200_read_data(struct archive_read *a, const void **buff, size_t *size, int6
 	if (AE_IFREG != (e->mode & AE_IFMT))
 		return (ARCHIVE_EOF);
 	if (e->zip_flags & (ZIP_ENCRYPTED | ZIP_STRONG_ENCRYPTED)) {
-		z->has_encrypted_entries = 1;
+		z->c.has_encrypted_entries = 1;
 		archive_set_error(&a->archive, ARCHIVE_ERRNO_FILE_FORMAT,
 		    "Encrypted ZIP entries are not supported by this build");
 		return (ARCHIVE_FAILED);
 	}
 	if (e->method != 0 && e->method != 8) {
 		archive_set_error(&a->archive, ARCHIVE_ERRNO_FILE_FORMAT,
-		    "Unsupported ZIP compression method (%d: %s)", e->method, compression_name(e->method));
+		    "Unsupported ZIP compression method (%d: %s)", e->method, zb_compression_name(e->method));
 		return (ARCHIVE_FAILED);
 	}
 	if (e->warn & B2I_ZW_TRUNCATED) {
@@ -522,7 +428,7 @@ zip_b200_read_data(struct archive_read *a, const void **buff, size_t *size, int6
 	}
 	/* end of entry: CRC, compressed size, uncompressed size - in this order (zip.c:3164-3194) */
 	z->end_of_entry = 1;
-	if ((r->flags & B2I_R_CRC_MISMATCH) && !z->ignore_crc32) {
+	if ((r->flags & B2I_R_CRC_MISMATCH) && !z->c.ignore_crc32) {
 		archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC, "ZIP bad CRC: 0x%lx should be 0x%lx",
 		    (unsigned long)r->crc, (unsigned long)e->crc32);
 		*size = 0; *buff = NULL;
@@ -568,8 +474,8 @@ zip_b200_cleanup(struct archive_read *a)
 	b2i_host_free(z->out);
 	if (z->have_index)
 		b2i_zip_index_free(&z->ix);
-	b2i_ctx_destroy(z->ctx);
-	archive_string_free(&z->format_name);
+	b2i_ctx_destroy(z->c.ctx);
+	archive_string_free(&z->c.format_name);
 	free(z);
 	a->format->data = NULL;
 	return (ARCHIVE_OK);
@@ -586,7 +492,7 @@ static int
 zip_b200_has_encrypted_entries(struct archive_read *a)
 {
 	if (a && a->format && a->format->data)
-		return (((struct zip_b200 *)a->format->data)->has_encrypted_entries);
+		return (((struct zip_b200 *)a->format->data)->c.has_encrypted_entries);
 	return (ARCHIVE_READ_FORMAT_ENCRYPTION_DONT_KNOW);
 }
 
@@ -604,7 +510,7 @@ archive_read_support_format_zip_seekable(struct archive *_a)
 		archive_set_error(&a->archive, ENOMEM, "Can't allocate zip data");
 		return (ARCHIVE_FATAL);
 	}
-	z->has_encrypted_entries = ARCHIVE_READ_FORMAT_ENCRYPTION_DONT_KNOW;
+	z->c.has_encrypted_entries = ARCHIVE_READ_FORMAT_ENCRYPTION_DONT_KNOW;
 	r = __archive_read_register_format(a, z, "zip", zip_b200_bid, zip_b200_options,
 	    zip_b200_read_header, zip_b200_read_data, zip_b200_read_data_skip, NULL, zip_b200_cleanup,
 	    zip_b200_capabilities, zip_b200_has_encrypted_entries);
@@ -613,18 +519,7 @@ archive_read_support_format_zip_seekable(struct archive *_a)
 	return (ARCHIVE_OK);
 }
 
-/* The streaming reader decodes entry N to learn where entry N+1 starts: serial by
- * construction and out of scope.  Registering nothing keeps
- * archive_read_support_format_zip() working; non-seekable input is then simply
- * not recognised as ZIP by this build. */
-int
-archive_read_support_format_zip_streamable(struct archive *_a)
-{
-	archive_check_magic(_a, ARCHIVE_READ_MAGIC, ARCHIVE_STATE_NEW,
-	    "archive_read_support_format_zip_streamable");
-	return (ARCHIVE_OK);
-}
-
+/* archive_read_support_format_zip_streamable: archive_read_support_format_zip_stream_b200.c */
 int
 archive_read_support_format_zip(struct archive *a)
 {

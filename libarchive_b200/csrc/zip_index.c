@@ -91,17 +91,19 @@ dos_time_slow(uint32_t d)
 
 struct cdrec {
 	uint64_t lho, csize, usize;
-	uint32_t crc, idx, mode;
-	int64_t  mtime;
+	uint32_t crc, idx, mode, uid, gid;
+	int64_t  mtime, atime, ctime;
 	uint16_t flags;
-	uint8_t  method;
+	uint8_t  method, system;
 };
 
-/* ZIP64 extended information, with the reference's order and conditions.
- * Returns 0, or -1 on the "Malformed 64-bit ..." / overflow conditions. */
+/* Extra fields, with the reference's order and conditions (zip.c:474-900): ZIP64
+ * sizes/offset (0x0001), times (0x5455, 0x5855), owner (0x5855, 0x7855, 0x7875)
+ * and the experimental attributes field (0x6c78).  The Unicode path (0x7075)
+ * needs the converted pathname and is left to the caller.  `with_lho`: central
+ * directory records only.  Returns 0, or -1 with *why set. */
 static int
-apply_extra(const uint8_t *p, size_t n, uint64_t *usize, uint64_t *csize, uint64_t *lho,
-    int64_t *mtime, const char **why)
+apply_extra(const uint8_t *p, size_t n, struct cdrec *r, int with_lho, const char **why)
 {
 	size_t off = 0;
 
@@ -120,26 +122,74 @@ apply_extra(const uint8_t *p, size_t n, uint64_t *usize, uint64_t *csize, uint64
 		o = off;
 		if (id == 0x0001) {
 			unsigned left = sz;
-			if (*usize == 0xffffffffull) {
+			if (r->usize == 0xffffffffull) {
 				uint64_t t;
 				if (left < 8 || (t = le64(p + o)) > INT64_MAX) { *why = "Malformed 64-bit uncompressed size"; return -1; }
-				*usize = t; o += 8; left -= 8;
+				r->usize = t; o += 8; left -= 8;
 			}
-			if (*csize == 0xffffffffull) {
+			if (r->csize == 0xffffffffull) {
 				uint64_t t;
 				if (left < 8 || (t = le64(p + o)) > INT64_MAX) { *why = "Malformed 64-bit compressed size"; return -1; }
-				*csize = t; o += 8; left -= 8;
+				r->csize = t; o += 8; left -= 8;
 			}
-			if (lho && *lho == 0xffffffffull) {
+			if (with_lho && r->lho == 0xffffffffull) {
 				uint64_t t;
 				if (left < 8 || (t = le64(p + o)) > INT64_MAX) { *why = "Malformed 64-bit local header offset"; return -1; }
-				*lho = t; o += 8; left -= 8;
+				r->lho = t; o += 8; left -= 8;
 			}
-		} else if (id == 0x5455 && sz >= 1) {
-			/* extended timestamp: mtime first when flag bit 0 is set */
-			if ((p[o] & 1) && sz >= 5)
-				*mtime = (int32_t)le32(p + o + 1);
+		} else if (id == 0x5455) {
+			unsigned left = sz;
+			int fl;
+			if (left == 0) { *why = "Incomplete extended time field"; return -1; }
+			fl = p[o++]; left--;
+			if (fl & 1) { if (left >= 4) { r->mtime = le32(p + o); o += 4; left -= 4; } else goto next; }
+			if (fl & 2) { if (left >= 4) { r->atime = le32(p + o); o += 4; left -= 4; } else goto next; }
+			if (fl & 4) { if (left >= 4) { r->ctime = le32(p + o); o += 4; left -= 4; } else goto next; }
+		} else if (id == 0x5855) {
+			if (sz >= 8) { r->atime = le32(p + o); r->mtime = le32(p + o + 4); }
+			if (sz >= 12) { r->uid = le16(p + o + 8); r->gid = le16(p + o + 10); }
+		} else if (id == 0x7855) {
+			if (sz >= 2) r->uid = le16(p + o);
+			if (sz >= 4) r->gid = le16(p + o + 2);
+		} else if (id == 0x7875) {
+			unsigned us = 0, gs;
+			if (sz >= 1 && p[o] == 1) {
+				if (sz >= 4) {
+					us = p[o + 1];
+					if (us == 2) r->uid = le16(p + o + 2);
+					else if (us == 4 && sz >= 6) r->uid = le32(p + o + 2);
+				}
+				if (sz >= 2 + us + 3) {
+					gs = p[o + 2 + us];
+					if (gs == 2) r->gid = le16(p + o + 2 + us + 1);
+					else if (gs == 4 && sz >= 2 + us + 5) r->gid = le32(p + o + 2 + us + 1);
+				}
+			}
+		} else if (id == 0x6c78) {
+			unsigned left = sz;
+			int bitmap, last;
+			if (left < 1) goto next;
+			last = bitmap = p[o++]; left--;
+			while ((last & 0x80) && left >= 1) { last = p[o++]; left--; }
+			if (bitmap & 1) { if (left < 2) goto next; r->system = (uint8_t)(le16(p + o) >> 8); o += 2; left -= 2; }
+			if (bitmap & 2) { if (left < 2) goto next; o += 2; left -= 2; }
+			if (bitmap & 4) {
+				uint32_t ext;
+				if (left < 4) goto next;
+				ext = le32(p + o);
+				if (r->system == 3)
+					r->mode = ext >> 16;
+				else if (r->system == 0) {
+					r->mode = (ext & 0x10) ? (IFDIR | 0775) : (IFREG | 0664);
+					if (ext & 0x01)
+						r->mode &= 0555;
+				} else
+					r->mode = 0;
+			}
+		} else if (id == 0x9901) {
+			if (sz < 6) { *why = "Incomplete AES field"; return -1; }
 		}
+next:
 		off += sz;
 	}
 	return 0;
@@ -264,7 +314,9 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 		const char *why = NULL;
 		uint64_t lho32 = le32(p + 42);
 
+		memset(r, 0, sizeof(*r));
 		r->idx = (uint32_t)k;
+		r->system = p[5];
 		r->flags = le16(p + 8);
 		if (r->flags & (ZIP_ENCRYPTED | ZIP_STRONG_ENCRYPTED))
 			out->has_encrypted_entries = 1;
@@ -284,7 +336,7 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 				r->mode &= 0555 | IFMT;
 		} else
 			r->mode = 0;
-		if (apply_extra(p + 46 + nl, xl, &r->usize, &r->csize, &r->lho, &r->mtime, &why) != 0) {
+		if (apply_extra(p + 46 + nl, xl, r, 1, &why) != 0) {
 			free(recs);
 			return err(errbuf, why);
 		}
@@ -323,6 +375,10 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 		e->method = r->method;
 		e->mode = r->mode;
 		e->mtime = r->mtime;
+		e->atime = r->atime;
+		e->ctime = r->ctime;
+		e->uid = r->uid;
+		e->gid = r->gid;
 		if (r->lho > size || size - r->lho < 30) {
 			e->warn |= B2I_ZW_TRUNCATED;
 			continue;
@@ -337,10 +393,15 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 			e->warn |= B2I_ZW_TRUNCATED;
 			continue;
 		}
-		uint64_t l_usize = le32(p + 22), l_csize = le32(p + 18);
+		uint64_t l_usize, l_csize;
 		uint32_t l_crc = le32(p + 14);
-		int64_t l_mtime = dos_time(&memo, le32(p + 10));
+		struct cdrec l = *r;     /* what the central record said stays unless the local header overrides it */
 		const char *why = NULL;
+
+		l.usize = le32(p + 22);
+		l.csize = le32(p + 18);
+		l.mtime = dos_time(&memo, le32(p + 10));
+		l.system = p[5];
 
 		e->version = p[4];
 		e->system = p[5];
@@ -350,11 +411,21 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 		e->name_len = (uint16_t)nl;
 		memcpy(names + names_len, p + 30, nl);
 		names_len += nl;
-		if (apply_extra(p + 30 + nl, xl, &l_usize, &l_csize, NULL, &l_mtime, &why) != 0) {
+		e->local_extra_offset = r->lho + 30 + nl;
+		e->local_extra_len = (uint16_t)xl;
+		if (apply_extra(p + 30 + nl, xl, &l, 0, &why) != 0) {
 			e->warn |= B2I_ZW_BAD_LOCAL_HEADER;
 			continue;
 		}
-		e->mtime = l_mtime;
+		l_usize = l.usize;
+		l_csize = l.csize;
+		e->mtime = l.mtime;
+		e->atime = l.atime;
+		e->ctime = l.ctime;
+		e->uid = l.uid;
+		e->gid = l.gid;
+		e->mode = l.mode;
+		e->system = l.system;
 		e->data_offset = r->lho + 30 + nl + xl;
 		/* central values are definitive; local ones win when present (zip.c:1106-1150) */
 		e->zip_flags &= (uint16_t)~ZIP_LENGTH_AT_END;

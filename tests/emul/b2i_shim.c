@@ -29,6 +29,13 @@ void *b2i_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void b2i_host_free(void *p) { free(p); }
 void b2i_free(void *p) { free(p); }
 
+int b2i_crc32(b2i_ctx *c, uint32_t crc, const void *buf, size_t len, uint32_t *out)
+{
+	(void)c;
+	*out = orc_crc32(crc, buf, len);
+	return B2I_OK;
+}
+
 int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes, const b2i_stream_desc *descs,
     size_t n, void *host_out, size_t out_bytes, b2i_stream_result *results)
 {

@@ -48,11 +48,27 @@ def run_one(binary, test, timeout=300):
         return f"FAIL({asserts.group(1) if asserts else '?'})", text[-8000:]
 
 
-def main(argv):
+# Tests the drop-in is NOT expected to pass, with the reason: features
+# outside the hot path that this build refuses instead of decoding on the CPU.
+KNOWN_GAPS = {
+    "test_read_format_zip_mac_metadata": "Mac resource-fork folding (mac-ext) not provided",
+    "test_read_format_zip_ppmd8_crash_1": "ZIPX PPMd (method 98) not provided",
+    "test_read_format_zip_ppmd8_crash_2": "ZIPX PPMd (method 98) not provided",
+    "test_read_format_zip_ppmd_multi": "ZIPX PPMd (method 98) not provided",
+    "test_read_format_zip_ppmd_multi_blockread": "ZIPX PPMd (method 98) not provided",
+    "test_read_format_zip_ppmd_one_file": "ZIPX PPMd (method 98) not provided",
+    "test_read_format_zip_ppmd_one_file_blockread": "ZIPX PPMd (method 98) not provided",
+    "test_read_format_zip_traditional_encryption_data": "PKWARE decryption not provided",
+    "test_write_format_zip_traditional_pkware_encryption": "PKWARE decryption not provided",
+}
+
+
+def main(argv, variant="dropin"):
     ref = os.path.join(REFDIR, "libarchive_test_ref")
-    drop = os.path.join(REFDIR, "libarchive_test_dropin")
-    only = argv[1:]
-    tests = [t for t in list_tests(ref) if not only or any(o in t for o in only)]
+    drop = os.path.join(REFDIR, "libarchive_test_" + variant)
+    only = [x for x in argv[1:] if not x.startswith("-")]
+    skip = [x[1:] for x in argv[1:] if x.startswith("-")]
+    tests = [t for t in list_tests(ref) if (not only or any(o in t for o in only)) and not any(k in t for k in skip)]
     results, logs = {}, {}
     for t in tests:
         r, _ = run_one(ref, t)
@@ -67,7 +83,11 @@ def main(argv):
 
 
 if __name__ == "__main__":
-    res, logs = main(sys.argv)
+    variant = "dropin"
+    if "--hostlogic" in sys.argv:
+        sys.argv.remove("--hostlogic")
+        variant = "hostlogic"
+    res, logs = main(sys.argv, variant)
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     json.dump({"results": res, "logs": logs}, open(os.path.join(out, "refsuite.json"), "w"), indent=1)
