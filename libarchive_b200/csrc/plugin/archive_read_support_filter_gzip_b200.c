@@ -42,6 +42,7 @@
 #include "archive_read_private.h"
 
 #include "b200inflate.h"
+#include "b200_ctx_pool.h"
 #include <stdio.h>
 
 #define OUT_BLOCK      (64 * 1024)            /* gzip.c:314 */
@@ -49,6 +50,7 @@
 
 struct gz_b200 {
 	b2i_ctx        *ctx;
+	int             ctx_bad;      /* a device call failed: do not hand the context back */
 	unsigned char  *out;          /* pinned: decoded bytes of the current window */
 	size_t          out_cap, out_len, served;
 	int             eof;          /* no more members */
@@ -225,7 +227,7 @@ next_window(struct archive_read_filter *self)
 		}
 	}
 	if (g->ctx == NULL) {
-		int rc = b2i_ctx_create(0, NULL, &g->ctx);
+		int rc = b200_ctx_acquire(&g->ctx);
 		if (rc != B2I_OK) {
 			b2i_free(mem);
 			return (fatal(self, g, "No usable B200 device; this build has no CPU inflate"));
@@ -265,7 +267,7 @@ next_window(struct archive_read_filter *self)
 		rc = b2i_decode_host(g->ctx, p, in_used, d, m_used, dst, out, r);
 		if (rc != B2I_OK) {
 			free(d); free(r); b2i_free(mem);
-			return (fatal(self, g, b2i_last_error(g->ctx)));
+			{ g->ctx_bad = 1; return (fatal(self, g, b2i_last_error(g->ctx))); }
 		}
 		/* members are served back to back: close the 16-byte alignment gaps */
 		size_t w = 0;
@@ -347,7 +349,7 @@ next_window(struct archive_read_filter *self)
 				return (fatal(self, g, "Can't allocate data for gzip decompression"));
 			rc = b2i_decode_host(g->ctx, p, in_use, &d, 1, g->out + g->out_len, budget, &r);
 			if (rc != B2I_OK)
-				return (fatal(self, g, b2i_last_error(g->ctx)));
+				{ g->ctx_bad = 1; return (fatal(self, g, b2i_last_error(g->ctx))); }
 			if (r.status == B2I_S_BUF_ERROR && in_use < (size_t)avail) {
 				in_lim *= 2;                       /* more of what is buffered */
 				continue;
@@ -435,7 +437,7 @@ gz_close(struct archive_read_filter *self)
 	struct gz_b200 *g = (struct gz_b200 *)self->data;
 
 	b2i_host_free(g->out);
-	b2i_ctx_destroy(g->ctx);
+	b200_ctx_release(g->ctx, !g->ctx_bad);
 	free(g->name);
 	free(g);
 	return (ARCHIVE_OK);

@@ -41,6 +41,7 @@
 #include "archive_string.h"
 
 #include "b200inflate.h"
+#include "b200_ctx_pool.h"
 #include "zip_b200_local.h"
 
 struct zip_b200 {
@@ -122,7 +123,7 @@ zip_b200_decode_all(struct archive_read *a, struct zip_b200 *z)
 
 	if (z->decoded)
 		return (ARCHIVE_OK);
-	if (z->c.ctx == NULL && (rc = b2i_ctx_create(0, NULL, &z->c.ctx)) != B2I_OK) {
+	if (z->c.ctx == NULL && (rc = b200_ctx_acquire(&z->c.ctx)) != B2I_OK) {
 		archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC,
 		    "No usable B200 device (b2i_ctx_create: %d); this build has no CPU inflate", rc);
 		return (ARCHIVE_FATAL);
@@ -167,6 +168,7 @@ zip_b200_decode_all(struct archive_read *a, struct zip_b200 *z)
 	}
 	if (n != 0 && (rc = b2i_decode_host(z->c.ctx, z->image, z->image_len, z->descs, n, z->out, out,
 	    z->res)) != B2I_OK) {
+		z->c.ctx_bad = 1;
 		archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC, "B200 decode failed (%d): %s", rc,
 		    b2i_last_error(z->c.ctx));
 		return (ARCHIVE_FATAL);
@@ -474,7 +476,7 @@ zip_b200_cleanup(struct archive_read *a)
 	b2i_host_free(z->out);
 	if (z->have_index)
 		b2i_zip_index_free(&z->ix);
-	b2i_ctx_destroy(z->c.ctx);
+	b200_ctx_release(z->c.ctx, !z->c.ctx_bad);
 	archive_string_free(&z->c.format_name);
 	free(z);
 	a->format->data = NULL;

@@ -43,6 +43,7 @@
 #include "archive_time_private.h"
 
 #include "b200inflate.h"
+#include "b200_ctx_pool.h"
 #include "zip_b200_local.h"
 
 struct zs_b200 {
@@ -90,7 +91,7 @@ zs_need_ctx(struct archive_read *a, struct zs_b200 *z)
 {
 	int rc;
 
-	if (z->c.ctx == NULL && (rc = b2i_ctx_create(0, NULL, &z->c.ctx)) != B2I_OK) {
+	if (z->c.ctx == NULL && (rc = b200_ctx_acquire(&z->c.ctx)) != B2I_OK) {
 		archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC,
 		    "No usable B200 device (b2i_ctx_create: %d); this build has no CPU inflate", rc);
 		return (ARCHIVE_FATAL);
@@ -161,6 +162,7 @@ zs_decode_entry(struct archive_read *a, struct zs_b200 *z, int64_t known, int64_
 				break;
 			}
 			if ((rc = b2i_decode_host(z->c.ctx, p, in_len, &d, 1, z->out, cap, &z->res)) != B2I_OK) {
+				z->c.ctx_bad = 1;
 				archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC, "B200 decode failed (%d): %s", rc,
 				    b2i_last_error(z->c.ctx));
 				return (ARCHIVE_FATAL);
@@ -609,7 +611,7 @@ zs_cleanup(struct archive_read *a)
 	struct zs_b200 *z = (struct zs_b200 *)a->format->data;
 
 	b2i_host_free(z->out);
-	b2i_ctx_destroy(z->c.ctx);
+	b200_ctx_release(z->c.ctx, !z->c.ctx_bad);
 	archive_string_free(&z->c.format_name);
 	free(z);
 	a->format->data = NULL;

@@ -1,0 +1,7 @@
+/* b200_ctx_pool.h — see b200_ctx_pool.c */
+#ifndef B200_CTX_POOL_H
+#define B200_CTX_POOL_H
+#include "b200inflate.h"
+int  b200_ctx_acquire(b2i_ctx **out);   /* B2I_OK or the b2i_ctx_create error */
+void b200_ctx_release(b2i_ctx *c, int healthy);
+#endif

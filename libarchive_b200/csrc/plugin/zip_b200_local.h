@@ -22,6 +22,7 @@
 /* options and conversion state both readers keep (zip.c:3271-3318, 930-1003) */
 struct zb_common {
 	b2i_ctx   *ctx;
+	int        ctx_bad;               /* a device call failed: do not hand the context back */
 	int        ignore_crc32;
 	int        has_encrypted_entries;
 	int        init_default_conversion;

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import json
 import os
+import time
 import re
 import subprocess
 import sys
@@ -71,13 +72,17 @@ def main(argv, variant="dropin"):
     tests = [t for t in list_tests(ref) if (not only or any(o in t for o in only)) and not any(k in t for k in skip)]
     results, logs = {}, {}
     for t in tests:
+        t0 = time.time()
         r, _ = run_one(ref, t)
+        t1 = time.time()
         d, log = run_one(drop, t)
-        results[t] = (r, d)
+        t2 = time.time()
+        results[t] = (r, d, round(t1 - t0, 2), round(t2 - t1, 2))
         if d != r:
             logs[t] = log
-        print(f"{t:64s} ref={r:10s} dropin={d}", flush=True)
-    same = sum(1 for r, d in results.values() if r == d)
+        gap = "  (declared gap: %s)" % KNOWN_GAPS[t] if t in KNOWN_GAPS and d != r else ""
+        print(f"{t:60s} ref={r:8s} {t1 - t0:6.1f}s   {variant}={d:10s} {t2 - t1:6.1f}s{gap}", flush=True)
+    same = sum(1 for v in results.values() if v[0] == v[1])
     print(f"== {same} of {len(results)} tests give the same verdict on both libraries")
     return results, logs
 

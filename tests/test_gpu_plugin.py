@@ -23,8 +23,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 with open(os.path.join(GOLD, "ref_expected.json")) as f:
     EXPECTED = json.load(f)
 
-# what this build refuses or leaves to the (out of scope) streaming reader
-STREAMING_ONLY = {"test_read_format_zip_extra_padding.zip", "test_read_format_zip_malformed1.zip"}
+# what this build refuses
 REFUSED = {"test_read_format_zip_encryption_data.zip"}       # different (still FAILED) message
 
 
@@ -58,9 +57,6 @@ def test_reference_fixture_through_the_dropin(name):
     exp = EXPECTED[name]
     path = os.path.join(GOLD, "ref_fixtures", name)
     lines, data = run(DROPIN, path, raw=exp["raw"])
-    if name in STREAMING_ONLY:
-        assert "open" in lines[0] and lines[0]["open"] == -30       # not recognised: no streaming reader
-        return
     want = exp["report"]
     assert len(lines) == len(want), (lines, want)
     for g, w in zip(lines, want):
