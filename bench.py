@@ -256,6 +256,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    # one process per GPU: staging buffers on the GPU's own NUMA node (multi-socket boxes)
+    from libarchive_b200.shard import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 and not os.environ.get("B2I_NO_NUMA_BIND") else 0
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -386,7 +389,7 @@ def main():
         "config": {"workload": args.workload, "description": WORKLOADS[args.workload],
                    "streams_per_gpu": n, "out_bytes_per_gpu": usize, "in_bytes_per_gpu": csize,
                    "l2": "working set (in+out %.0f MB) exceeds the 126 MB L2; no flush" % ((usize + csize) / 1e6),
-                   "parallelism": "entries sharded by rank, no collective", "scale": args.scale},
+                   "parallelism": "entries sharded by rank, no collective", "scale": args.scale, "numa_bound_cpus": numa_cpus},
         "roofline": {"bound": "hbm", "kernel": "b2i_inflate_kernel" if args.workload != "stored1m" else "b2i_crc_chunks_kernel",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,

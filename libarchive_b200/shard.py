@@ -41,3 +41,25 @@ def shard_descs(descs, rank: int, world: int):
         d.out_off = out
         out = (out + int(d.out_cap) + 15) & ~15
     return capi.make_descs(items), in_lo, in_hi, out, (lo, hi)
+
+
+def bind_to_gpu_numa(device_index: int):
+    """Pin this process to the CPUs next to GPU `device_index` (NVML's ideal CPU set) BEFORE
+    pinned host buffers are allocated: with one process per GPU, staging memory then lives on
+    the GPU's own NUMA node and host<->device copies do not cross the socket interconnect.
+    Returns the number of CPUs bound to, or 0 when nothing was changed (no NVML, one node...)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus or len(cpus) >= len(os.sched_getaffinity(0)):
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
