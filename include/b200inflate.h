@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B2I_ABI_VERSION 2
+#define B2I_ABI_VERSION 3
 
 /* ---- return codes of the API functions -------------------------------- */
 #define B2I_OK            0
@@ -151,6 +151,22 @@ void b2i_plan_destroy(b2i_plan *);
 int  b2i_decode_host(b2i_ctx *, const void *host_in, size_t in_bytes,
                      const b2i_stream_desc *descs, size_t n,
                      void *host_out, size_t out_bytes, b2i_stream_result *res);
+
+/* The same, split in two so that a reader working through several archives (or
+ * one archive in pieces) keeps the device and both directions of the host link
+ * busy: b2i_submit queues copy-in, kernels and copy-out and returns; b2i_wait
+ * blocks until the job's last byte has landed in host_out, fills res[n] and
+ * releases the job.  Up to two jobs of one context may be in flight, so the
+ * copy-out of one overlaps the copy-in and decode of the next; a third submit
+ * fails with B2I_E_INVAL.  The descriptors are copied by b2i_submit; host_in and
+ * host_out must stay valid (and should be pinned, b2i_host_alloc) until b2i_wait
+ * returns.  Replaces the reference's one-entry-at-a-time inflate loop
+ * (archive_read_support_format_zip.c:2535-2690) the same way b2i_decode_host does. */
+typedef struct b2i_job b2i_job;
+int  b2i_submit(b2i_ctx *, const void *host_in, size_t in_bytes,
+                const b2i_stream_desc *descs, size_t n,
+                void *host_out, size_t out_bytes, b2i_job **job);
+int  b2i_wait(b2i_job *job, b2i_stream_result *res /* n entries */);
 
 /* ---- scalar drop-ins --------------------------------------------------------
  * b2i_crc32: same contract as zlib crc32()/archive_crc32.h:43-84:

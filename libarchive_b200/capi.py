@@ -58,7 +58,7 @@ EXPORTS = [
     "b2i_ctx_create", "b2i_ctx_destroy", "b2i_last_error", "b2i_abi_version", "b2i_device_count",
     "b2i_ctx_sync", "b2i_ctx_launch_count", "b2i_host_alloc", "b2i_host_free", "b2i_device_alloc",
     "b2i_device_free", "b2i_memcpy_h2d", "b2i_memcpy_d2h", "b2i_plan_create", "b2i_plan_launch",
-    "b2i_plan_results", "b2i_plan_destroy", "b2i_decode_host", "b2i_crc32", "b2i_crc32_device",
+    "b2i_plan_results", "b2i_plan_destroy", "b2i_decode_host", "b2i_submit", "b2i_wait", "b2i_crc32", "b2i_crc32_device",
     "b2i_crc32_combine", "b2i_zip_index_build", "b2i_zip_index_free", "b2i_gzip_peek_header",
     "b2i_gzip_scan_bgzf", "b2i_free",
 ]
@@ -101,6 +101,8 @@ def lib():
     L.b2i_plan_destroy.argtypes = [vp]
     L.b2i_plan_destroy.restype = None
     L.b2i_decode_host.argtypes = [vp, vp, sz, C.POINTER(StreamDesc), sz, vp, sz, C.POINTER(StreamResult)]
+    L.b2i_submit.argtypes = [vp, vp, sz, C.POINTER(StreamDesc), sz, vp, sz, C.POINTER(vp)]
+    L.b2i_wait.argtypes = [vp, C.POINTER(StreamResult)]
     L.b2i_crc32.argtypes = [vp, u32, vp, sz, C.POINTER(u32)]
     L.b2i_crc32_device.argtypes = [vp, u32, vp, sz, C.POINTER(u32)]
     L.b2i_crc32_combine.argtypes = [u32, u32, u64]
@@ -162,6 +164,20 @@ class Context:
         res = (StreamResult * n)()
         self._check(self.L.b2i_decode_host(self.h, _addr(host_in), in_bytes, descs, n,
                                            _addr(host_out), out_bytes, res))
+        return res
+
+    def submit(self, host_in, in_bytes: int, descs, host_out, out_bytes: int):
+        """b2i_submit: returns a job handle for wait(); at most two may be in flight."""
+        job = C.c_void_p()
+        self._check(self.L.b2i_submit(self.h, _addr(host_in), in_bytes, descs, len(descs),
+                                      _addr(host_out), out_bytes, C.byref(job)))
+        return (job, len(descs))
+
+    def wait(self, job):
+        """b2i_wait: blocks until the job's output is in host memory; returns its results."""
+        handle, n = job
+        res = (StreamResult * max(n, 1))()
+        self._check(self.L.b2i_wait(handle, res))
         return res
 
     def crc32(self, data: bytes, crc: int = 0) -> int:

@@ -30,6 +30,22 @@ static_assert(offsetof(b2i_stream_result, detail) == offsetof(B2iResult, detail)
 #define B2I_PIPE_STREAMS 4
 #define B2I_PIPE_SLICES  12
 
+struct b2i_plan;
+#define B2I_MAX_JOBS 2
+/* one host-buffer decode in flight: its own device staging, plan arena and events,
+ * so that the copy-out of one job overlaps the copy-in and kernels of the next */
+struct b2i_job {
+	struct b2i_ctx *ctx;
+	bool busy, ev_ready;
+	uint8_t *d_in;  size_t d_in_cap;
+	uint8_t *d_out; size_t d_out_cap;
+	uint8_t *arena_d; uint8_t *arena_h; size_t arena_cap;
+	cudaEvent_t ev_in[B2I_PIPE_SLICES], ev_k[B2I_PIPE_SLICES], ev_done;
+	b2i_plan *plans[B2I_PIPE_SLICES];
+	size_t cut[B2I_PIPE_SLICES + 1];
+	size_t K, n;
+};
+
 struct b2i_ctx {
 	int device;
 	int num_sms;
@@ -52,6 +68,7 @@ struct b2i_ctx {
 	cudaEvent_t ev_in[B2I_PIPE_SLICES], ev_k[B2I_PIPE_SLICES], ev_free;
 	bool pipe_ready;
 	uint8_t *arena_d; uint8_t *arena_h; size_t arena_cap;
+	b2i_job jobs[B2I_MAX_JOBS];     /* host-buffer decodes in flight (b2i_submit / b2i_wait) */
 	char err[256];
 };
 
@@ -170,6 +187,20 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 	cudaFree(c->d_out);
 	cudaFree(c->arena_d);
 	cudaFreeHost(c->arena_h);
+	for (int i = 0; i < B2I_MAX_JOBS; i++) {
+		b2i_job *J = &c->jobs[i];
+		for (size_t k = 0; k < B2I_PIPE_SLICES; k++)
+			if (J->plans[k])
+				b2i_plan_destroy(J->plans[k]);
+		cudaFree(J->d_in);
+		cudaFree(J->d_out);
+		cudaFree(J->arena_d);
+		cudaFreeHost(J->arena_h);
+		if (J->ev_ready) {
+			for (int k = 0; k < B2I_PIPE_SLICES; k++) { cudaEventDestroy(J->ev_in[k]); cudaEventDestroy(J->ev_k[k]); }
+			cudaEventDestroy(J->ev_done);
+		}
+	}
 	if (c->s_team) cudaStreamDestroy(c->s_team);
 	if (c->pipe_ready) {
 		cudaStreamDestroy(c->s_in);
@@ -535,19 +566,19 @@ static int ensure_pipe(b2i_ctx *c)
 	return B2I_OK;
 }
 
-static int ensure_arena(b2i_ctx *c, size_t need)
+static int ensure_arena(b2i_ctx *c, b2i_job *J, size_t need)
 {
-	if (c->arena_cap >= need)
+	if (J->arena_cap >= need)
 		return B2I_OK;
 	cudaDeviceSynchronize();
-	cudaFree(c->arena_d);
-	cudaFreeHost(c->arena_h);
-	c->arena_d = NULL; c->arena_h = NULL; c->arena_cap = 0;
+	cudaFree(J->arena_d);
+	cudaFreeHost(J->arena_h);
+	J->arena_d = NULL; J->arena_h = NULL; J->arena_cap = 0;
 	need += need / 2;
-	if (cudaMalloc(&c->arena_d, need) != cudaSuccess ||
-	    cudaHostAlloc((void **)&c->arena_h, need, cudaHostAllocDefault) != cudaSuccess)
+	if (cudaMalloc(&J->arena_d, need) != cudaSuccess ||
+	    cudaHostAlloc((void **)&J->arena_h, need, cudaHostAllocDefault) != cudaSuccess)
 		return fail(c, B2I_E_NOMEM, "plan arena of %zu bytes", need);
-	c->arena_cap = need;
+	J->arena_cap = need;
 	return B2I_OK;
 }
 
@@ -557,25 +588,69 @@ static int ensure_arena(b2i_ctx *c, size_t need)
  * the copy-in stream, decoded on a compute stream as soon as its bytes have
  * landed (the slice kernels are small enough to be co-resident), and copied
  * out on the copy-out stream as soon as its kernel is done - so H2D of slice
- * s+1, the kernel of slice s and D2H of slice s-1 overlap.  Synchronous.
+ * s+1, the kernel of slice s and D2H of slice s-1 overlap.
+ *
+ * b2i_submit queues all of that and returns; b2i_wait blocks until the job's
+ * last copy has landed and hands out the results.  Up to B2I_MAX_JOBS jobs of
+ * one context may be in flight: they share the three streams (so copies of one
+ * direction stay in submission order) and own their device staging, so the
+ * copy-out of job k overlaps the copy-in and kernels of job k+1.
+ * b2i_decode_host is submit + wait.
  */
-extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
-    const b2i_stream_desc *descs, size_t n, void *host_out, size_t out_bytes,
-    b2i_stream_result *res)
+static void job_drain(b2i_ctx *c, b2i_job *J)
 {
-	if (c == NULL)
+	cudaStreamSynchronize(c->s_out);
+	cudaStreamSynchronize(c->s_in);
+	for (int i = 0; i < B2I_PIPE_STREAMS; i++)
+		cudaStreamSynchronize(c->s_cmp[i]);
+	for (size_t s = 0; s < B2I_PIPE_SLICES; s++) {
+		if (J->plans[s])
+			b2i_plan_destroy(J->plans[s]);
+		J->plans[s] = NULL;
+	}
+	J->busy = false;
+}
+
+extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
+    const b2i_stream_desc *descs, size_t n, void *host_out, size_t out_bytes, b2i_job **job)
+{
+	if (c == NULL || job == NULL)
 		return B2I_E_INVAL;
-	if (n == 0)
-		return B2I_OK;
-	if (host_in == NULL || descs == NULL || res == NULL)
-		return fail(c, B2I_E_INVAL, "b2i_decode_host: NULL argument");
+	*job = NULL;
+	if (n != 0 && (host_in == NULL || descs == NULL))
+		return fail(c, B2I_E_INVAL, "b2i_submit: NULL argument");
+	b2i_job *J = NULL;
+	for (int i = 0; i < B2I_MAX_JOBS && J == NULL; i++)
+		if (!c->jobs[i].busy)
+			J = &c->jobs[i];
+	if (J == NULL)
+		return fail(c, B2I_E_INVAL, "b2i_submit: %d jobs already in flight on this context", B2I_MAX_JOBS);
+	J->ctx = c;
+	J->n = n;
+	J->K = 0;
+	for (size_t s = 0; s < B2I_PIPE_SLICES; s++)
+		J->plans[s] = NULL;
 	CU(c, cudaSetDevice(c->device));
 	int rc;
-	if ((rc = ensure_dev(c, &c->d_in, &c->d_in_cap, in_bytes)) != B2I_OK)
-		return rc;
-	if ((rc = ensure_dev(c, &c->d_out, &c->d_out_cap, out_bytes)) != B2I_OK)
-		return rc;
 	if ((rc = ensure_pipe(c)) != B2I_OK)
+		return rc;
+	if (!J->ev_ready) {
+		for (int i = 0; i < B2I_PIPE_SLICES; i++) {
+			CU(c, cudaEventCreateWithFlags(&J->ev_in[i], cudaEventDisableTiming));
+			CU(c, cudaEventCreateWithFlags(&J->ev_k[i], cudaEventDisableTiming));
+		}
+		CU(c, cudaEventCreateWithFlags(&J->ev_done, cudaEventDisableTiming));
+		J->ev_ready = true;
+	}
+	if (n == 0) {
+		J->busy = true;
+		CU(c, cudaEventRecord(J->ev_done, c->s_out));
+		*job = J;
+		return B2I_OK;
+	}
+	if ((rc = ensure_dev(c, &J->d_in, &J->d_in_cap, in_bytes)) != B2I_OK)
+		return rc;
+	if ((rc = ensure_dev(c, &J->d_out, &J->d_out_cap, out_bytes)) != B2I_OK)
 		return rc;
 
 	/* slices: contiguous descriptor ranges of about equal csize + usize */
@@ -604,7 +679,7 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 				frac[k] = (double)(k + 1) / (double)K;
 		}
 	}
-	size_t cut[B2I_PIPE_SLICES + 1];
+	size_t *cut = J->cut;
 	{
 		uint64_t acc = 0;
 		size_t k = 1;
@@ -625,11 +700,13 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		arena_need += align_up(plan_block_bound(cut[s + 1] - cut[s], stored_bytes), 256);
 	}
 	(void)per_slice;
-	if ((rc = ensure_arena(c, arena_need)) != B2I_OK)
+	if ((rc = ensure_arena(c, J, arena_need)) != B2I_OK)
 		return rc;
+	J->K = K;
 	/* work of an earlier call on the caller's stream (if any) comes first */
 	CU(c, cudaEventRecord(c->ev_free, c->stream));
 	CU(c, cudaStreamWaitEvent(c->s_in, c->ev_free, 0));
+	J->busy = true;
 
 	/* Experimental (B2I_MIRROR=1): when host_out is pinned the inflate kernel can
 	 * store every 16-byte unit to it as well, so decoded bytes cross the host link
@@ -647,7 +724,7 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 			if (descs[i].method == B2I_METHOD_STORED && !(descs[i].flags & B2I_F_NO_COPY))
 				mirror = NULL;
 	}
-	b2i_plan *plans[B2I_PIPE_SLICES] = { 0 };
+	b2i_plan **plans = J->plans;
 	rc = B2I_OK;
 	for (size_t s = 0; s < K && rc == B2I_OK; s++) {
 		const b2i_stream_desc *sd = descs + cut[s];
@@ -658,7 +735,7 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		/* copy-in stream, in order: this slice's plan block, then its bytes.  (Copies
 		 * of one direction execute in submission order, so the small plan upload
 		 * must not queue behind later slices' data.) */
-		rc = b2i_plan_build(c, sd, sn, cs, c->s_in, c->arena_d + arena_off[s], c->arena_h + arena_off[s],
+		rc = b2i_plan_build(c, sd, sn, cs, c->s_in, J->arena_d + arena_off[s], J->arena_h + arena_off[s],
 		    align_up(plan_block_bound(sn, stored_bytes), 256), &plans[s]);
 		if (rc != B2I_OK)
 			break;
@@ -671,20 +748,20 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		}
 		if (lo < hi) {
 			lo &= ~(uint64_t)15;
-			cudaError_t e = cudaMemcpyAsync(c->d_in + lo, (const uint8_t *)host_in + lo, hi - lo,
+			cudaError_t e = cudaMemcpyAsync(J->d_in + lo, (const uint8_t *)host_in + lo, hi - lo,
 			    cudaMemcpyHostToDevice, c->s_in);
 			if (e != cudaSuccess) { rc = fail(c, B2I_E_CUDA, "H2D: %s", cudaGetErrorString(e)); break; }
 		}
-		if (cudaEventRecord(c->ev_in[s], c->s_in) != cudaSuccess ||
-		    cudaStreamWaitEvent(cs, c->ev_in[s], 0) != cudaSuccess) {
+		if (cudaEventRecord(J->ev_in[s], c->s_in) != cudaSuccess ||
+		    cudaStreamWaitEvent(cs, J->ev_in[s], 0) != cudaSuccess) {
 			rc = fail(c, B2I_E_CUDA, "event"); break;
 		}
 		plans[s]->out_mirror = mirror;
-		rc = b2i_plan_launch(plans[s], c->d_in, in_bytes, c->d_out, out_bytes);
+		rc = b2i_plan_launch(plans[s], J->d_in, in_bytes, J->d_out, out_bytes);
 		if (rc != B2I_OK)
 			break;
-		if (cudaEventRecord(c->ev_k[s], cs) != cudaSuccess ||
-		    cudaStreamWaitEvent(c->s_out, c->ev_k[s], 0) != cudaSuccess) {
+		if (cudaEventRecord(J->ev_k[s], cs) != cudaSuccess ||
+		    cudaStreamWaitEvent(c->s_out, J->ev_k[s], 0) != cudaSuccess) {
 			rc = fail(c, B2I_E_CUDA, "event"); break;
 		}
 		/* copy-out stream, in order: the slice's decoded bytes, then its results */
@@ -698,7 +775,7 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 				}
 			}
 			if (olo < ohi && ohi <= out_bytes) {
-				cudaError_t e = cudaMemcpyAsync((uint8_t *)host_out + olo, c->d_out + olo, ohi - olo,
+				cudaError_t e = cudaMemcpyAsync((uint8_t *)host_out + olo, J->d_out + olo, ohi - olo,
 				    cudaMemcpyDeviceToHost, c->s_out);
 				if (e != cudaSuccess) { rc = fail(c, B2I_E_CUDA, "D2H: %s", cudaGetErrorString(e)); break; }
 			}
@@ -709,22 +786,55 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		}
 	}
 	/* everything funnels into the copy-out stream (it waited on every slice's kernel) */
-	cudaError_t e1 = cudaStreamSynchronize(c->s_out);
-	cudaError_t e2 = cudaStreamSynchronize(c->s_in);
-	for (int i = 0; i < B2I_PIPE_STREAMS; i++)
-		if (cudaStreamSynchronize(c->s_cmp[i]) != cudaSuccess)
-			e1 = cudaErrorUnknown;
-	if (rc == B2I_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
-		rc = fail(c, B2I_E_CUDA, "pipeline: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-	for (size_t s = 0; s < K; s++) {
-		if (plans[s] == NULL)
+	if (rc == B2I_OK && cudaEventRecord(J->ev_done, c->s_out) != cudaSuccess)
+		rc = fail(c, B2I_E_CUDA, "event");
+	if (rc != B2I_OK) {
+		job_drain(c, J);
+		return rc;
+	}
+	*job = J;
+	return B2I_OK;
+}
+
+extern "C" int b2i_wait(b2i_job *J, b2i_stream_result *res)
+{
+	if (J == NULL || !J->busy)
+		return B2I_E_INVAL;
+	b2i_ctx *c = J->ctx;
+	int rc = B2I_OK;
+	cudaError_t e = cudaEventSynchronize(J->ev_done);
+	if (e != cudaSuccess)
+		rc = fail(c, B2I_E_CUDA, "pipeline: %s", cudaGetErrorString(e));
+	if (rc == B2I_OK && J->n != 0 && res == NULL)
+		rc = fail(c, B2I_E_INVAL, "b2i_wait: NULL results");
+	for (size_t s = 0; s < J->K; s++) {
+		if (J->plans[s] == NULL)
 			continue;
 		if (rc == B2I_OK)
-			memcpy(res + cut[s], plans[s]->h_block + plans[s]->results_off,
-			    (cut[s + 1] - cut[s]) * sizeof(B2iResult));
-		b2i_plan_destroy(plans[s]);
+			memcpy(res + J->cut[s], J->plans[s]->h_block + J->plans[s]->results_off,
+			    (J->cut[s + 1] - J->cut[s]) * sizeof(B2iResult));
+		b2i_plan_destroy(J->plans[s]);
+		J->plans[s] = NULL;
 	}
+	J->busy = false;
 	return rc;
+}
+
+extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
+    const b2i_stream_desc *descs, size_t n, void *host_out, size_t out_bytes,
+    b2i_stream_result *res)
+{
+	if (c == NULL)
+		return B2I_E_INVAL;
+	if (n == 0)
+		return B2I_OK;
+	if (host_in == NULL || descs == NULL || res == NULL)
+		return fail(c, B2I_E_INVAL, "b2i_decode_host: NULL argument");
+	b2i_job *J = NULL;
+	int rc = b2i_submit(c, host_in, in_bytes, descs, n, host_out, out_bytes, &J);
+	if (rc != B2I_OK)
+		return rc;
+	return b2i_wait(J, res);
 }
 
 /* ---- scalar CRC drop-ins ---------------------------------------------------- */

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_binding as ob
-from libarchive_b200 import capi, synth
+from libarchive_b200 import capi, reader, synth
 from libarchive_b200.capi import StreamDesc
 
 pytestmark = pytest.mark.gpu
@@ -297,3 +297,37 @@ def test_team_decoder_opt_in(ctx, monkeypatch):
     caps[4] = 250000
     out = run_streams(ctx, streams, caps=caps, lead=5, gap=3)
     compare(names, *out)
+
+
+def test_two_jobs_in_flight(ctx):
+    """b2i_submit / b2i_wait: two host-buffer decodes of one context overlap; results and
+    bytes equal the one-call path and the oracle; a third submit is refused."""
+    import ctypes as C
+    L = capi.lib()
+    batches = []
+    for seed in (1, 2, 3):
+        members = [synth.ZipMember("f%d_%d" % (seed, i), synth.synth_text(30000 + 1000 * i, 10 * seed + i)) for i in range(40)]
+        members.append(synth.ZipMember("bad", synth.synth_text(5000, seed), crc=123))
+        z = synth.make_zip(members)
+        entries, _, _ = capi.zip_index(z)
+        descs, out_bytes, _ = reader.plan_zip(entries, stored_no_copy=False)
+        h_in = L.b2i_host_alloc(len(z) + 64)
+        h_out = L.b2i_host_alloc(out_bytes + 64)
+        C.memmove(h_in, z, len(z))
+        batches.append((z, descs, out_bytes, h_in, h_out))
+    jobs = [ctx.submit(b[3], len(b[0]), b[1], b[4], b[2]) for b in batches[:2]]
+    with pytest.raises(capi.B2IError):
+        ctx.submit(batches[2][3], len(batches[2][0]), batches[2][1], batches[2][4], batches[2][2])
+    results = [ctx.wait(jobs[0])]
+    jobs.append(ctx.submit(batches[2][3], len(batches[2][0]), batches[2][1], batches[2][4], batches[2][2]))
+    results += [ctx.wait(jobs[1]), ctx.wait(jobs[2])]
+    for (z, descs, out_bytes, h_in, h_out), res in zip(batches, results):
+        ores, oout = ob.decode_batch(z, descs, out_bytes)
+        got = C.string_at(h_out, out_bytes)
+        for k in range(len(descs)):
+            assert (res[k].status, res[k].crc, res[k].out_bytes, res[k].in_bytes, res[k].flags) == \
+                   (ores[k].status, ores[k].crc, ores[k].out_bytes, ores[k].in_bytes, ores[k].flags), k
+            o, nb = descs[k].out_off, res[k].out_bytes
+            assert got[o:o + nb] == oout[o:o + nb], k
+        L.b2i_host_free(h_in)
+        L.b2i_host_free(h_out)

@@ -24,7 +24,7 @@ def test_abi_exports_match_header():
     for name in sorted(declared):
         assert hasattr(L, name), "header declares %s but the library does not export it" % name
     assert declared == set(capi.EXPORTS)
-    assert L.b2i_abi_version() == 2
+    assert L.b2i_abi_version() == 3
 
 
 def test_struct_layouts():
