@@ -7,7 +7,7 @@
  * archive_read_support_format_zip / _raw, archive_read_support_filter_gzip,
  * archive_read_open_memory, archive_read_next_header, archive_read_data_block.
  *
- *   oracle_extract list  <file> [--raw] [--opt zip:ignorecrc32] [--dump out.bin]
+ *   oracle_extract list  <file> [--raw] [--opt zip:ignorecrc32] [--dump out.bin] [--stream BLOCK]
  *       one JSON line per entry: name, size, header/read return codes, bytes
  *       read, CRC-32 (zlib) of the bytes read, block sizes, error string
  *   oracle_extract bench <file> [--raw] --procs P [--reps R]
@@ -80,6 +80,22 @@ json_str(FILE *f, const char *s)
 	fputc('"', f);
 }
 
+/* --stream N: hand the bytes out in N-byte blocks through a read callback only
+ * (no seek, no skip), so that the ZIP STREAMING reader is the one that runs */
+static struct { const unsigned char *p; size_t left, blk; } g_src;
+static int g_stream_blk;
+
+static la_ssize_t
+stream_read(struct archive *a, void *cd, const void **buff)
+{
+	size_t n = g_src.left < g_src.blk ? g_src.left : g_src.blk;
+	(void)a; (void)cd;
+	*buff = g_src.p;
+	g_src.p += n;
+	g_src.left -= n;
+	return (la_ssize_t)n;
+}
+
 static struct archive *
 open_reader(const void *buf, size_t len, int raw, const char *opt)
 {
@@ -95,7 +111,13 @@ open_reader(const void *buf, size_t len, int raw, const char *opt)
 		fprintf(stderr, "set_options: %s\n", archive_error_string(a));
 		exit(2);
 	}
-	if (archive_read_open_memory(a, buf, len) != ARCHIVE_OK) {
+	if (g_stream_blk > 0) {
+		g_src.p = buf;
+		g_src.left = len;
+		g_src.blk = (size_t)g_stream_blk;
+	}
+	if ((g_stream_blk > 0 ? archive_read_open(a, NULL, NULL, stream_read, NULL) :
+	    archive_read_open_memory(a, buf, len)) != ARCHIVE_OK) {
 		printf("{\"open\":%d,\"err\":", -30);
 		json_str(stdout, archive_error_string(a));
 		printf("}\n");
@@ -350,6 +372,7 @@ main(int argc, char **argv)
 		else if (!strcmp(argv[i], "--procs") && i + 1 < argc) procs = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--reps") && i + 1 < argc) reps = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--limit") && i + 1 < argc) limit = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--stream") && i + 1 < argc) g_stream_blk = atoi(argv[++i]);
 	}
 	buf = slurp(argv[2], &len);
 	if (!strcmp(argv[1], "list"))

@@ -1,0 +1,63 @@
+"""Generated archives and the comparison rule for the STREAMING ZIP reader (non-seekable
+input), shared by the no-GPU test (plugin host logic over the oracle shim) and the GPU test
+(the real drop-in).  Both are compared with the unmodified reference driven the same way."""
+import json
+import os
+import subprocess
+import tempfile
+import zlib
+
+from libarchive_b200 import synth
+
+
+def archive(framing):
+    txt = synth.synth_text(300000, 11)
+    comp = synth.deflate_raw(txt, 6)
+    crc = zlib.crc32(txt) & 0xFFFFFFFF
+    members = [synth.ZipMember("dir/", b"", method=0), synth.ZipMember("dir/ok.txt", txt),
+               synth.ZipMember("stored.bin", synth.synth_random(70000, 3), method=0),
+               synth.ZipMember("empty", b"", method=0),
+               synth.ZipMember("fixed.txt", txt[:5000], level=1, strategy=zlib.Z_FIXED),
+               synth.ZipMember("crc.txt", txt[:40000], crc=crc ^ 1), synth.ZipMember("last.txt", txt[:777])]
+    if framing == "sizes":       # sizes in the local header: the checks that need them
+        members[5:5] = [synth.ZipMember("junk.txt", txt, comp=comp + b"JUNKJUNK"),
+                        synth.ZipMember("usize.txt", txt, usize=len(txt) + 1),
+                        synth.ZipMember("bt3.txt", txt, comp=bytes([comp[0] | 6]) + comp[1:])]
+    return synth.make_zip(members, framing=framing)
+
+
+def report(binary, blob, block, opt=None):
+    with tempfile.NamedTemporaryFile(suffix=".zip", delete=False) as f:
+        f.write(blob)
+    try:
+        cmd = [binary, "list", f.name, "--stream", str(block)] + (["--opt", opt] if opt else [])
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return [json.loads(l) for l in r.stdout.splitlines() if l.strip()]
+    finally:
+        os.unlink(f.name)
+
+
+def comparable(lines):
+    """The reference's block sizes in streaming mode follow the input chunks zlib was fed; this
+    build decodes an entry whole and serves 256 KiB blocks.  So block counts / sizes are not
+    compared, nor - for an entry that FAILS - how many bytes went out before the failing block.
+    Names, sizes, modes, times, return codes, messages, and bytes + CRC of good entries are."""
+    out = []
+    for l in lines:
+        d = {k: v for k, v in l.items() if k not in ("nblk", "blocks")}
+        if d.get("rd", 1) < 0:
+            d.pop("nbytes", None)
+            d.pop("crc", None)
+        out.append(d)
+    return out
+
+
+def check(ref_binary, new_binary):
+    for framing in ("sizes", "at_end"):
+        z = archive(framing)
+        for block in (977, 65536, 1 << 24):
+            for blob, opt in ((z, None), (z, "zip:ignorecrc32"), (z[:len(z) // 3], None)):
+                a = comparable(report(ref_binary, blob, block, opt))
+                b = comparable(report(new_binary, blob, block, opt))
+                assert a == b, (framing, block, opt, len(blob), a, b)

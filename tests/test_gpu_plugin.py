@@ -27,9 +27,11 @@ with open(os.path.join(GOLD, "ref_expected.json")) as f:
 REFUSED = {"test_read_format_zip_encryption_data.zip"}       # different (still FAILED) message
 
 
-def run(binary, path, raw=False, opt=None, env=None):
+def run(binary, path, raw=False, opt=None, env=None, stream=0):
     dump = path + ".dump." + os.path.basename(binary)
     cmd = [binary, "list", path, "--dump", dump]
+    if stream:
+        cmd += ["--stream", str(stream)]      # read callback only: the ZIP streaming reader runs
     if raw:
         cmd.append("--raw")
     if opt:
@@ -68,15 +70,15 @@ def test_reference_fixture_through_the_dropin(name):
         assert hashlib.sha256(data).hexdigest() == exp["data_sha256"]
 
 
-def both(blob, raw=False, opt=None, env=None):
+def both(blob, raw=False, opt=None, env=None, stream=0):
     need_dropin()
     if not ob.have_ref():
         pytest.skip("oracle/_ref not built")
     with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
         f.write(blob)
     try:
-        a = run(ob.REF_EXTRACT, f.name, raw, opt)
-        b = run(DROPIN, f.name, raw, opt, env)
+        a = run(ob.REF_EXTRACT, f.name, raw, opt, None, stream)
+        b = run(DROPIN, f.name, raw, opt, env, stream)
     finally:
         os.unlink(f.name)
     return a, b
@@ -130,3 +132,13 @@ def test_bgzf_and_plain_gzip_identical_reports():
     (ra, da), (rb, db) = both(bytes(bad), raw=True, env={"B2I_GZIP_VERIFY": "1"})
     if ra[0].get("rd") == 1:
         assert rb[0].get("rd", rb[0].get("open")) == -30
+
+
+def test_streaming_reader_identical_reports():
+    """Non-seekable input: the streaming ZIP reader (local headers, data descriptors) of the
+    drop-in against the reference's, on generated archives with good and bad entries."""
+    need_dropin()
+    if not ob.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import stream_cases
+    stream_cases.check(ob.REF_EXTRACT, DROPIN)

@@ -40,3 +40,16 @@ def test_reference_tests_pass_on_plugin_host_logic(tmp_path):
     assert n >= 125, text[-2000:]
     unexpected = failing - set(KNOWN_GAPS)
     assert not unexpected, "reference tests failing outside the declared gaps: %s" % sorted(unexpected)
+
+
+def test_streaming_reader_reports_match_reference():
+    """Generated archives read through a read callback only (no seeking): the streaming reader's
+    host logic against the unmodified reference - good entries, data descriptors, bad CRC, wrong
+    sizes, junk after the stream, invalid block type, truncation."""
+    ref, new = os.path.join(REFDIR, "oracle_extract"), os.path.join(REFDIR, "hostlogic_extract")
+    if not (os.path.exists(ref) and os.path.exists(new)):
+        pytest.skip("oracle/_ref drivers not built (needs /root/reference)")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import stream_cases
+    stream_cases.check(ref, new)
