@@ -16,7 +16,7 @@
 #else
 #include <cuda_runtime.h>
 #define B2I_DEV __device__ __forceinline__
-#define B2I_DEV_NOINLINE __device__ __noinline__
+#define B2I_DEV_NOINLINE static __device__ __noinline__
 B2I_DEV unsigned b2i_lane() { unsigned l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
 #endif
 

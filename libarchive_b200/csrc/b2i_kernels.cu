@@ -19,8 +19,18 @@
 
 #include <stdio.h>
 #define INFLATE_WARPS 4
+#ifdef B2I_R9
+/* second build of this file: only the single-warp inflate kernel and its launch
+ * wrapper, under other names (see inflate_core.cuh) */
+#define INFLATE_CTAS 8
+#define b2i_inflate_kernel b2i_inflate_kernel_r9
+#define b2i_launch_inflate b2i_launch_inflate_r9
+#else
+#define INFLATE_CTAS 7
+#endif
+#define INFLATE_SLOTS 64u      /* token regions per SM: twice the resident warps of the larger build */
 
-#ifdef B2I_PHASE_CLOCKS
+#if defined(B2I_PHASE_CLOCKS) && !defined(B2I_R9)
 __global__ void b2i_phase_dump_kernel()
 {
 	printf("B2I_PHASE header=%llu lpdec=%llu lpres=%llu unif=%llu crc=%llu batches=%llu stored=%llu\n",
@@ -31,7 +41,7 @@ __global__ void b2i_phase_dump_kernel()
 void b2i_phase_dump(cudaStream_t st) { b2i_phase_dump_kernel<<<1, 1, 0, st>>>(); }
 #endif
 
-extern "C" __global__ void __launch_bounds__(INFLATE_WARPS * 32, 7)
+extern "C" __global__ void __launch_bounds__(INFLATE_WARPS * 32, INFLATE_CTAS)
 b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *__restrict__ out,
     uint8_t *__restrict__ out_mirror,
     const B2iDesc *__restrict__ descs, B2iResult *__restrict__ results,
@@ -53,7 +63,7 @@ b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *_
 		if (lane == 0) {
 			unsigned smid;
 			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-			slot = (smid * 56u + (blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5)) % 56u) % nslots;
+			slot = (smid * INFLATE_SLOTS + (blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5)) % INFLATE_SLOTS) % nslots;
 			while (atomicCAS(&slot_busy[slot], 0u, 1u) != 0u)
 				slot = slot + 1 == nslots ? 0 : slot + 1;
 		}
@@ -80,6 +90,7 @@ b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *_
 	}
 }
 
+#ifndef B2I_R9
 /*
  * K1 for LARGE streams: one CTA (TEAM_WARPS warps) per stream, see inflate_team.cuh.
  * Warp 0 pulls streams from the counter and owns them; the other warps serve its
@@ -103,7 +114,7 @@ b2i_inflate_team_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8
 	if (lane == 0) {
 		unsigned smid;
 		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-		slot = (smid * 56u + (blockIdx.x * TEAM_WARPS + w) % 56u) % nslots;
+		slot = (smid * INFLATE_SLOTS + (blockIdx.x * TEAM_WARPS + w) % INFLATE_SLOTS) % nslots;
 		while (atomicCAS(&slot_busy[slot], 0u, 1u) != 0u)
 			slot = slot + 1 == nslots ? 0 : slot + 1;
 		ts->scratch[w] = scratch + (size_t)slot * LP_SCRATCH_WORDS;
@@ -342,7 +353,7 @@ b2i_tables_kernel(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, uint32_t *la
 
 size_t b2i_inflate_smem_bytes(void) { return sizeof(WarpSmem) * INFLATE_WARPS; }
 /* token scratch for a launch on `num_sms` SMs (every resident warp owns one region) */
-uint32_t b2i_inflate_scratch_slots(int num_sms) { return (uint32_t)num_sms * 56u; }
+uint32_t b2i_inflate_scratch_slots(int num_sms) { return (uint32_t)num_sms * INFLATE_SLOTS; }
 size_t b2i_inflate_scratch_bytes(int num_sms)
 {
 	return (size_t)b2i_inflate_scratch_slots(num_sms) * LP_SCRATCH_WORDS * sizeof(uint32_t);
@@ -355,13 +366,15 @@ cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, 
 	return cudaGetLastError();
 }
 
+#endif /* !B2I_R9 */
+
 cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out, uint8_t *out_mirror,
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
     unsigned int *slot_busy, int num_sms, cudaStream_t st)
 {
 	static bool configured = false;
-	const size_t smem = b2i_inflate_smem_bytes();
+	const size_t smem = sizeof(WarpSmem) * INFLATE_WARPS;
 	if (!configured) {
 		cudaError_t e = cudaFuncSetAttribute(b2i_inflate_kernel,
 		    cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -374,7 +387,7 @@ cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *ou
 		configured = true;
 	}
 	uint32_t blocks = (n + INFLATE_WARPS - 1) / INFLATE_WARPS;
-	uint32_t max_blocks = (uint32_t)num_sms * 7u;
+	uint32_t max_blocks = (uint32_t)num_sms * INFLATE_CTAS;
 	if (blocks > max_blocks)
 		blocks = max_blocks;
 	b2i_inflate_kernel<<<blocks, INFLATE_WARPS * 32, smem, st>>>(in, in_total, out, out_mirror, descs,
@@ -382,6 +395,7 @@ cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *ou
 	return cudaGetLastError();
 }
 
+#ifndef B2I_R9
 cudaError_t b2i_launch_inflate_team(const uint8_t *in, uint64_t in_total, uint8_t *out, uint8_t *out_mirror,
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
@@ -438,3 +452,4 @@ cudaError_t b2i_launch_unsupported(const B2iDesc *descs, B2iResult *results,
 	b2i_unsupported_kernel<<<(n + 127) / 128, 128, 0, st>>>(descs, results, list, n);
 	return cudaGetLastError();
 }
+#endif /* !B2I_R9 */

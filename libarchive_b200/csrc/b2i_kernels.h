@@ -27,6 +27,11 @@ cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *ou
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
     unsigned int *slot_busy, int num_sms, cudaStream_t st);
+/* the 9-bit-root / 8-CTA build of the same kernel (launches with several waves of streams) */
+cudaError_t b2i_launch_inflate_r9(const uint8_t *in, uint64_t in_total, uint8_t *out, uint8_t *out_mirror,
+    const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
+    unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
+    unsigned int *slot_busy, int num_sms, cudaStream_t st);
 cudaError_t b2i_launch_inflate_team(const uint8_t *in, uint64_t in_total, uint8_t *out, uint8_t *out_mirror,
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,

@@ -34,10 +34,19 @@
 #include "b2i_common.cuh"
 #include "crc32_core.cuh"
 
+/* Two builds of the single-warp kernel (b2i_kernels.cu is compiled twice):
+ *   default  10-bit lit/len root, 7 CTAs x 4 warps per SM - fastest per stream;
+ *   B2I_R9    9-bit root (smaller tables), 8 CTAs per SM at 64 registers - more
+ *             resident warps, which pays when a launch has several waves of streams. */
+#ifdef B2I_R9
+#define LIT_ROOT    9
+#define LIT_TABLE   856    /* >= 852 = max over complete 286-symbol codes, root 9 (the fixed code needs 512) */
+#else
 #define LIT_ROOT    10
+#define LIT_TABLE   1336   /* >= 1334 = max over complete 288-symbol codes   */
+#endif
 #define DIST_ROOT   8
 #define CL_ROOT     7
-#define LIT_TABLE   1336   /* >= 1334 = max over complete 288-symbol codes   */
 #define DIST_TABLE  400    /* max over complete 30/32-symbol codes, root 8   */
 #define RING_HALF   128
 #define RING_BYTES  (2 * RING_HALF)

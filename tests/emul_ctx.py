@@ -12,16 +12,20 @@ from libarchive_b200.capi import StreamResult
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "emul", "libemul.so")
 _emu = None
+_libs = {}
+VARIANT = ""          # "" = default build, "r9" = the 9-bit-root build of the inflate kernel
 
 
 def emu():
     global _emu
-    if _emu is None:
+    if VARIANT not in _libs:
         subprocess.run(["make", "-C", os.path.join(HERE, "emul")], check=True, stdout=subprocess.DEVNULL)
-        _emu = C.CDLL(SO)
-        _emu.emul_crc32.restype = C.c_uint32
-        _emu.emul_crc32.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64]
-        _emu.emul_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib = C.CDLL(SO if not VARIANT else SO.replace("libemul.so", "libemul_%s.so" % VARIANT))
+        lib.emul_crc32.restype = C.c_uint32
+        lib.emul_crc32.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64]
+        lib.emul_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        _libs[VARIANT] = lib
+    _emu = _libs[VARIANT]
     return _emu
 
 

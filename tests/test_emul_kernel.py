@@ -124,3 +124,19 @@ def test_team_decoder_small_cases():
         assert r.status == o.status and ed == od, (name, r.status, o.status)
         if o.status == 0:
             assert r.in_bytes == o.in_bytes and r.crc == (zlib.crc32(od) & 0xFFFFFFFF), name
+
+
+def test_nine_bit_root_build(monkeypatch):
+    """The second build of the inflate kernel (B2I_R9: 9-bit lit/len root, 856-entry table):
+    same streams, same answers - including codes with 10..15-bit symbols that now live in
+    secondary tables."""
+    import emul_ctx
+    monkeypatch.setattr(emul_ctx, "VARIANT", "r9")
+    for name, s in synth.deflate_zoo():
+        check(name, s, leads=(0,))
+    for seed in range(12):
+        check("rand%d" % seed, synth.random_dynamic_stream(300 + seed, 1200), leads=(seed % 16,))
+    txt = synth.synth_text(70000, 5)
+    check("text", synth.deflate_raw(txt[:65536], 9), leads=(7,))
+    check("fixed", synth.deflate_raw(txt[:9000], 6, zlib.Z_FIXED), leads=(1,))
+    check("cut", synth.deflate_raw(txt[:30000], 6)[:4000], leads=(2,))

@@ -331,3 +331,34 @@ def test_two_jobs_in_flight(ctx):
             assert got[o:o + nb] == oout[o:o + nb], k
         L.b2i_host_free(h_in)
         L.b2i_host_free(h_out)
+
+
+def test_nine_bit_root_kernel(ctx, monkeypatch):
+    """The second build of the inflate kernel (b2i_inflate_kernel_r9: 9-bit lit/len root, 8 CTAs
+    per SM; picked for batches with several waves of streams) forced onto the zoo, random codes,
+    mutated streams and real text: identical results."""
+    monkeypatch.setenv("B2I_KERNEL", "r9")
+    zoo = [(n, s) for n, s in synth.deflate_zoo()]
+    compare([n for n, _ in zoo], *run_streams(ctx, [s for _, s in zoo], lead=3))
+    streams = [synth.random_dynamic_stream(seed, 2500) for seed in range(200, 280)]
+    compare(["rand%d" % i for i in range(len(streams))], *run_streams(ctx, streams, lead=1, gap=1))
+    rng = np.random.default_rng(5)
+    txt = synth.synth_text(300000, 21)
+    base = [synth.deflate_raw(txt[:70000], 6), synth.deflate_raw(txt, 9), synth.deflate_raw(txt[:70000], 6, zlib.Z_FIXED)]
+    streams = list(base)
+    for k in range(200):
+        s = bytearray(base[k % len(base)])
+        for _ in range(int(rng.integers(1, 6))):
+            pos = int(rng.integers(0, len(s) * 8))
+            s[pos >> 3] ^= 1 << (pos & 7)
+        streams.append(bytes(s))
+    compare(["m%d" % i for i in range(len(streams))], *run_streams(ctx, streams, caps=[1 << 19] * len(streams), lead=2, gap=5))
+
+
+def test_many_waves_pick_the_second_build(ctx):
+    """12 000 small streams (> 2 waves of 148 x 28 warps): the API picks the 8-CTA build by
+    itself; results equal the oracle's."""
+    txt = synth.synth_text(1 << 20, 4)
+    streams = [synth.deflate_raw(txt[(i * 131) % 900000:][:2000 + (i % 7) * 300], 6) for i in range(12000)]
+    out = run_streams(ctx, streams, caps=[8192] * len(streams), lead=0, gap=0)
+    compare(["s%d" % i for i in range(len(streams))], *out)
