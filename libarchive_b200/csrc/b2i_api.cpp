@@ -58,16 +58,14 @@ struct b2i_ctx {
 	unsigned int *d_slot_busy;   /* one flag per token region */
 	uint32_t *d_scratch;   /* token regions of the lane-parallel decoder, one per resident warp */
 	uint64_t launches;
-	/* grow-only staging for b2i_decode_host / b2i_crc32 */
+	/* grow-only staging for b2i_crc32 (host buffers) */
 	uint8_t *d_in;  size_t d_in_cap;
-	uint8_t *d_out; size_t d_out_cap;
 	/* pipelined host path: copy-in / compute / copy-out streams, and a reusable
 	 * (grow-only) arena for the slice plans so that no call allocates */
 	cudaStream_t s_in, s_out, s_cmp[B2I_PIPE_STREAMS];
 	cudaStream_t s_team;     /* large streams (one CTA each) run beside the single-warp kernel */
-	cudaEvent_t ev_in[B2I_PIPE_SLICES], ev_k[B2I_PIPE_SLICES], ev_free;
+	cudaEvent_t ev_free;
 	bool pipe_ready;
-	uint8_t *arena_d; uint8_t *arena_h; size_t arena_cap;
 	b2i_job jobs[B2I_MAX_JOBS];     /* host-buffer decodes in flight (b2i_submit / b2i_wait) */
 	char err[256];
 };
@@ -185,9 +183,6 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 	cudaFree(c->d_ztab);
 	cudaFree(c->d_lane_mul);
 	cudaFree(c->d_in);
-	cudaFree(c->d_out);
-	cudaFree(c->arena_d);
-	cudaFreeHost(c->arena_h);
 	for (int i = 0; i < B2I_MAX_JOBS; i++) {
 		b2i_job *J = &c->jobs[i];
 		for (size_t k = 0; k < B2I_PIPE_SLICES; k++)
@@ -207,7 +202,6 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 		cudaStreamDestroy(c->s_in);
 		cudaStreamDestroy(c->s_out);
 		for (int i = 0; i < B2I_PIPE_STREAMS; i++) cudaStreamDestroy(c->s_cmp[i]);
-		for (int i = 0; i < B2I_PIPE_SLICES; i++) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_k[i]); }
 		cudaEventDestroy(c->ev_free);
 	}
 	if (c->own_stream)
@@ -565,10 +559,6 @@ static int ensure_pipe(b2i_ctx *c)
 	CU(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
 	for (int i = 0; i < B2I_PIPE_STREAMS; i++)
 		CU(c, cudaStreamCreateWithFlags(&c->s_cmp[i], cudaStreamNonBlocking));
-	for (int i = 0; i < B2I_PIPE_SLICES; i++) {
-		CU(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
-		CU(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
-	}
 	CU(c, cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming));
 	c->pipe_ready = true;
 	return B2I_OK;

@@ -165,13 +165,13 @@ make_room(struct gz_b200 *g, size_t need)
 	size_t pending = g->out_len - g->served;
 
 	if (pending + need + 16 > g->out_cap) {
-		size_t cap = pending + need + 16 + ((pending + need) >> 2);
-		unsigned char *nb = b2i_host_alloc(cap);
+		size_t cap = 0;
+		unsigned char *nb = b200_buf_acquire(pending + need + 16 + ((pending + need) >> 2), &cap);
 		if (nb == NULL)
 			return (-1);
 		if (pending)
 			memcpy(nb, g->out + g->served, pending);
-		b2i_host_free(g->out);
+		b200_buf_release(g->out, g->out_cap);
 		g->out = nb;
 		g->out_cap = cap;
 	} else if (g->served && pending) {
@@ -436,7 +436,7 @@ gz_close(struct archive_read_filter *self)
 {
 	struct gz_b200 *g = (struct gz_b200 *)self->data;
 
-	b2i_host_free(g->out);
+	b200_buf_release(g->out, g->out_cap);
 	b200_ctx_release(g->ctx, !g->ctx_bad);
 	free(g->name);
 	free(g);

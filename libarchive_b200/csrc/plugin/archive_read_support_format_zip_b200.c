@@ -53,7 +53,7 @@ struct zip_b200 {
 	size_t             *desc_of;       /* entry -> descriptor index, or SIZE_MAX */
 	size_t              ndesc;
 	unsigned char      *out;           /* pinned: decoded bytes of the batch */
-	size_t              out_bytes;
+	size_t              out_bytes, out_cap;
 	unsigned char     **retry;         /* per descriptor: private buffer after an overflow retry */
 	const unsigned char *image;        /* the whole archive, as handed out by the read core */
 	size_t              image_len;
@@ -161,7 +161,7 @@ zip_b200_decode_all(struct archive_read *a, struct zip_b200 *z)
 	}
 	z->ndesc = n;
 	z->out_bytes = out;
-	z->out = b2i_host_alloc(out + 16);
+	z->out = b200_buf_acquire(out + 16, &z->out_cap);
 	if (z->out == NULL) {
 		archive_set_error(&a->archive, ENOMEM, "No memory for ZIP decompression");
 		return (ARCHIVE_FATAL);
@@ -473,7 +473,7 @@ zip_b200_cleanup(struct archive_read *a)
 	free(z->descs);
 	free(z->res);
 	free(z->desc_of);
-	b2i_host_free(z->out);
+	b200_buf_release(z->out, z->out_cap);
 	if (z->have_index)
 		b2i_zip_index_free(&z->ix);
 	b200_ctx_release(z->c.ctx, !z->c.ctx_bad);

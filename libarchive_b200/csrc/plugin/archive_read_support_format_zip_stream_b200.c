@@ -138,10 +138,9 @@ zs_decode_entry(struct archive_read *a, struct zs_b200 *z, int64_t known, int64_
 		if (cap < 65536 && expect_out <= 0)
 			cap = 65536;
 		for (;;) {
-			if (z->out == NULL || z->out_cap < cap) {
-				b2i_host_free(z->out);
-				z->out_cap = cap;
-				if ((z->out = b2i_host_alloc(cap + 16)) == NULL) {
+			if (z->out == NULL || z->out_cap < cap + 16) {
+				b200_buf_release(z->out, z->out_cap);
+				if ((z->out = b200_buf_acquire(cap + 16, &z->out_cap)) == NULL) {
 					z->out_cap = 0;
 					archive_set_error(&a->archive, ENOMEM, "No memory for ZIP decompression");
 					return (ARCHIVE_FATAL);
@@ -610,7 +609,7 @@ zs_cleanup(struct archive_read *a)
 {
 	struct zs_b200 *z = (struct zs_b200 *)a->format->data;
 
-	b2i_host_free(z->out);
+	b200_buf_release(z->out, z->out_cap);
 	b200_ctx_release(z->c.ctx, !z->c.ctx_bad);
 	archive_string_free(&z->c.format_name);
 	free(z);

@@ -8,6 +8,11 @@
  * uses one context at a time (libarchive handles are single-threaded,
  * README.md:217-220), different handles may live on different threads, hence
  * the lock.
+ *
+ * The same goes for the pinned host buffers the decoded bytes land in: pinning
+ * memory costs about as much per byte as decoding it (a 256 MiB cudaHostAlloc
+ * takes longer than the whole device pass), so buffers are kept and handed to the
+ * next handle that needs one.
  */
 #include <pthread.h>
 #include <stddef.h>
@@ -51,4 +56,59 @@ b200_ctx_release(b2i_ctx *c, int healthy)
 	pthread_mutex_unlock(&pool_lock);
 	if (c != NULL)
 		b2i_ctx_destroy(c);
+}
+
+/* ---- pinned output buffers ---------------------------------------------------- */
+#define BUF_MAX    4
+#define BUF_KEEP   ((size_t)2 << 30)     /* total bytes kept idle at most */
+
+static struct { void *p; size_t cap; } bufs[BUF_MAX];
+static int bufs_n;
+
+void *
+b200_buf_acquire(size_t need, size_t *cap)
+{
+	void *p = NULL;
+	int best = -1;
+
+	pthread_mutex_lock(&pool_lock);
+	for (int i = 0; i < bufs_n; i++)
+		if (bufs[i].cap >= need && (best < 0 || bufs[i].cap < bufs[best].cap))
+			best = i;
+	if (best >= 0) {
+		p = bufs[best].p;
+		*cap = bufs[best].cap;
+		bufs[best] = bufs[--bufs_n];
+	}
+	pthread_mutex_unlock(&pool_lock);
+	if (p != NULL)
+		return (p);
+	/* some headroom, so that a slightly larger archive next time still fits */
+	*cap = need + need / 8 + 4096;
+	if ((p = b2i_host_alloc(*cap)) == NULL) {
+		*cap = need;
+		p = b2i_host_alloc(need);
+	}
+	return (p);
+}
+
+void
+b200_buf_release(void *p, size_t cap)
+{
+	size_t idle = 0;
+
+	if (p == NULL)
+		return;
+	pthread_mutex_lock(&pool_lock);
+	for (int i = 0; i < bufs_n; i++)
+		idle += bufs[i].cap;
+	if (bufs_n < BUF_MAX && idle + cap <= BUF_KEEP) {
+		bufs[bufs_n].p = p;
+		bufs[bufs_n].cap = cap;
+		bufs_n++;
+		p = NULL;
+	}
+	pthread_mutex_unlock(&pool_lock);
+	if (p != NULL)
+		b2i_host_free(p);
 }
