@@ -60,7 +60,22 @@ struct zs_b200 {
 	size_t              out_cap;
 	b2i_stream_result   res;
 	int64_t             delivered;     /* bytes of `out` already returned             */
+	const unsigned char *cur;          /* the decoded bytes being served: `out` or a slot of the batch */
+	/* look-ahead batch: deflate entries with known sizes that follow the current one in
+	 * the read-ahead buffer, decoded in the same device pass (zs_batch_decode) */
+	struct {
+		size_t             n, next;        /* entries, first one not taken yet */
+		int64_t           *pos;            /* absolute input position of each entry's data */
+		b2i_stream_desc   *d;
+		b2i_stream_result *r;
+		unsigned char     *out;
+		size_t             out_cap, cap_n;
+	} b;
 };
+
+#define ZS_BATCH_MAX_ENTRIES 4096
+#define ZS_BATCH_MAX_IN      ((size_t)64 << 20)
+#define ZS_BATCH_MAX_OUT     ((size_t)256 << 20)
 
 /* ---- bid (zip.c:3345-3380) ------------------------------------------------------ */
 static int
@@ -183,7 +198,149 @@ zs_decode_entry(struct archive_read *a, struct zs_b200 *z, int64_t known, int64_
 	z->cread = (int64_t)z->res.in_bytes;
 	z->decoded = 1;
 	z->delivered = 0;
+	z->cur = z->out;
 	return (ARCHIVE_OK);
+}
+
+/*
+ * Entries of a streamed archive are discovered one header at a time, but when
+ * the sizes are in the local headers (no length-at-end flag) the headers that
+ * follow can be read ahead without decoding anything.  The first data request
+ * of a deflate entry therefore walks the local headers behind it as far as the
+ * read core can provide bytes (bounded), makes one descriptor per plain deflate
+ * entry and decodes them all in ONE device pass; the entries that follow find
+ * their result here (matched by absolute input position, sizes and CRC as their
+ * own header states them) instead of paying a device round trip each.
+ * Returns 1 when the current entry was decoded as slot 0 of a new batch.
+ */
+static int
+zs_batch_decode(struct archive_read *a, struct zs_b200 *z)
+{
+	const int64_t here = archive_filter_bytes(&a->archive, 0);
+	const unsigned char *p;
+	ssize_t avail;
+	size_t o, n = 0, out = 0, total;
+	int rc;
+
+	if (z->remaining <= 0 || (size_t)z->remaining > ZS_BATCH_MAX_IN ||
+	    z->m.uncompressed_size > ZS_BATCH_MAX_OUT || z->m.uncompressed_size >= 0xffffffffu)
+		return (0);
+	if (z->b.cap_n == 0) {
+		z->b.pos = calloc(ZS_BATCH_MAX_ENTRIES, sizeof(*z->b.pos));
+		z->b.d = calloc(ZS_BATCH_MAX_ENTRIES, sizeof(*z->b.d));
+		z->b.r = calloc(ZS_BATCH_MAX_ENTRIES, sizeof(*z->b.r));
+		if (z->b.pos == NULL || z->b.d == NULL || z->b.r == NULL)
+			return (0);
+		z->b.cap_n = ZS_BATCH_MAX_ENTRIES;
+	}
+	z->b.n = z->b.next = 0;
+	/* slot 0: the current entry */
+	memset(&z->b.d[0], 0, sizeof(z->b.d[0]));
+	z->b.d[0].in_off = 0;
+	z->b.d[0].in_len = (uint64_t)z->remaining;
+	z->b.d[0].out_cap = z->m.uncompressed_size;
+	z->b.d[0].expect_out = z->m.uncompressed_size;
+	z->b.d[0].expect_crc = z->m.crc32;
+	z->b.d[0].method = 8;
+	z->b.d[0].flags = z->c.ignore_crc32 ? B2I_F_NO_CRC : 0;
+	z->b.d[0].out_off = 0;
+	z->b.pos[0] = here;
+	out = ((size_t)z->m.uncompressed_size + 15) & ~(size_t)15;
+	n = 1;
+	o = (size_t)z->remaining;
+	total = o;
+	/* the local headers that follow */
+	while (n < ZS_BATCH_MAX_ENTRIES) {
+		uint32_t flags, method, csize, usize, nl, xl, hcrc;
+
+		if ((p = __archive_read_ahead(a, o + 30, &avail)) == NULL)
+			break;
+		p += o;
+		if (memcmp(p, "PK\003\004", 4) != 0)
+			break;
+		flags = zb_le16(p + 6);
+		method = zb_le16(p + 8);
+		csize = zb_le32(p + 18);
+		usize = zb_le32(p + 22);
+		nl = zb_le16(p + 26);
+		xl = zb_le16(p + 28);
+		hcrc = zb_le32(p + 14);            /* the next look may move the buffer: p is not used below */
+		if ((flags & (ZIP_ENCRYPTED | ZIP_STRONG_ENCRYPTED | ZIP_LENGTH_AT_END)) ||
+		    csize == 0xffffffffu || usize == 0xffffffffu || (method != 0 && method != 8))
+			break;
+		if (o + 30 + nl + xl + csize > ZS_BATCH_MAX_IN || out + usize > ZS_BATCH_MAX_OUT)
+			break;
+		if (__archive_read_ahead(a, o + 30 + nl + xl + csize, &avail) == NULL)
+			break;                                  /* the body is not all there */
+		if (method == 8 && csize > 0) {
+			b2i_stream_desc *d = &z->b.d[n];
+			memset(d, 0, sizeof(*d));
+			d->in_off = o + 30 + nl + xl;
+			d->in_len = csize;
+			d->out_cap = usize;
+			d->expect_out = usize;
+			d->expect_crc = hcrc;
+			d->method = 8;
+			d->flags = z->c.ignore_crc32 ? B2I_F_NO_CRC : 0;
+			d->out_off = out;
+			z->b.pos[n] = here + (int64_t)d->in_off;
+			out += ((size_t)usize + 15) & ~(size_t)15;
+			n++;
+		}
+		o += 30 + nl + xl + csize;
+		total = o;
+	}
+	if (n < 2)
+		return (0);                                     /* nothing to gain: the plain path */
+	if ((p = __archive_read_ahead(a, total, &avail)) == NULL)
+		return (0);
+	if (zs_need_ctx(a, z) != ARCHIVE_OK)
+		return (0);
+	if (z->b.out == NULL || z->b.out_cap < out + 16) {
+		b200_buf_release(z->b.out, z->b.out_cap);
+		if ((z->b.out = b200_buf_acquire(out + 16, &z->b.out_cap)) == NULL) {
+			z->b.out_cap = 0;
+			return (0);
+		}
+	}
+	if ((rc = b2i_decode_host(z->c.ctx, p, total, z->b.d, n, z->b.out, out, z->b.r)) != B2I_OK) {
+		z->c.ctx_bad = 1;
+		return (0);                                     /* the plain path reports the failure */
+	}
+	z->b.n = n;
+	z->b.next = 0;
+	return (1);
+}
+
+/* the current entry's result from the batch, if it is there: 1 = taken */
+static int
+zs_batch_take(struct archive_read *a, struct zs_b200 *z)
+{
+	const int64_t here = archive_filter_bytes(&a->archive, 0);
+	size_t k;
+
+	for (k = z->b.next; k < z->b.n; k++) {
+		const b2i_stream_desc *d = &z->b.d[k];
+		if (z->b.pos[k] < here)
+			continue;
+		if (z->b.pos[k] != here)
+			break;
+		z->b.next = k + 1;
+		if ((int64_t)d->in_len != z->remaining || d->expect_out != z->m.uncompressed_size ||
+		    d->expect_crc != z->m.crc32 || ((d->flags & B2I_F_NO_CRC) != 0) != (z->c.ignore_crc32 != 0) ||
+		    z->b.r[k].status == B2I_S_OUT_OVERFLOW)
+			return (0);             /* not what this entry's header says (or needs room): decode it alone */
+		z->res = z->b.r[k];
+		z->cur = z->b.out + d->out_off;
+		__archive_read_consume(a, (int64_t)z->res.in_bytes);
+		z->remaining -= (int64_t)z->res.in_bytes;
+		z->cread = (int64_t)z->res.in_bytes;
+		z->decoded = 1;
+		z->delivered = 0;
+		return (1);
+	}
+	z->b.next = k;
+	return (0);
 }
 
 /*
@@ -319,7 +476,7 @@ zs_local_header(struct archive_read *a, struct archive_entry *entry, struct zs_b
 				    m->method, zb_compression_name(m->method));
 				return (ARCHIVE_FAILED);
 			}
-			t = z->out;
+			t = z->cur;
 			full = (size_t)z->res.out_bytes;
 			len = 0;                        /* already consumed by the decode */
 		} else
@@ -493,7 +650,9 @@ zs_read_data(struct archive_read *a, const void **buff, size_t *size, int64_t *o
 
 		if (!z->decoded) {
 			int known = 0 == (m->zip_flags & ZIP_LENGTH_AT_END);
-			if (zs_decode_entry(a, z, known ? z->remaining : 0,
+			if (known && (zs_batch_take(a, z) || (zs_batch_decode(a, z) && zs_batch_take(a, z))))
+				;                       /* decoded together with its neighbours */
+			else if (zs_decode_entry(a, z, known ? z->remaining : 0,
 			    known ? (int64_t)m->uncompressed_size : 0) != ARCHIVE_OK)
 				return (ARCHIVE_FATAL);
 			z->computed_crc = z->res.crc;
@@ -518,7 +677,7 @@ zs_read_data(struct archive_read *a, const void **buff, size_t *size, int64_t *o
 			}
 			last = 0;
 		}
-		*buff = z->out + z->delivered;
+		*buff = z->cur + z->delivered;
 		*size = n;
 		z->delivered += (int64_t)n;
 		z->uread = z->delivered;
@@ -610,6 +769,10 @@ zs_cleanup(struct archive_read *a)
 	struct zs_b200 *z = (struct zs_b200 *)a->format->data;
 
 	b200_buf_release(z->out, z->out_cap);
+	b200_buf_release(z->b.out, z->b.out_cap);
+	free(z->b.pos);
+	free(z->b.d);
+	free(z->b.r);
 	b200_ctx_release(z->c.ctx, !z->c.ctx_bad);
 	archive_string_free(&z->c.format_name);
 	free(z);
