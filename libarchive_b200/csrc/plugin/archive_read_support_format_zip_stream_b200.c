@@ -193,6 +193,10 @@ zs_decode_entry(struct archive_read *a, struct zs_b200 *z, int64_t known, int64_
 		}
 		break;
 	}
+	/* a failed stream may report a position past its end (the bit reader runs ahead);
+	 * never consume more than it was given */
+	if (z->res.in_bytes > in_len)
+		z->res.in_bytes = in_len;
 	__archive_read_consume(a, (int64_t)z->res.in_bytes);
 	z->remaining -= (int64_t)z->res.in_bytes;
 	z->cread = (int64_t)z->res.in_bytes;
@@ -331,6 +335,8 @@ zs_batch_take(struct archive_read *a, struct zs_b200 *z)
 		    z->b.r[k].status == B2I_S_OUT_OVERFLOW)
 			return (0);             /* not what this entry's header says (or needs room): decode it alone */
 		z->res = z->b.r[k];
+		if (z->res.in_bytes > d->in_len)
+			z->res.in_bytes = d->in_len;
 		z->cur = z->b.out + d->out_off;
 		__archive_read_consume(a, (int64_t)z->res.in_bytes);
 		z->remaining -= (int64_t)z->res.in_bytes;
