@@ -178,6 +178,10 @@ zs_decode_entry(struct archive_read *a, struct zs_b200 *z, int64_t known, int64_
 		}
 		break;
 	}
+	/* a failed stream may report a position past its end (the bit reader runs ahead);
+	 * never consume more than it was given */
+	if (z->res.in_bytes > in_len)
+		z->res.in_bytes = in_len;
 	__archive_read_consume(a, (int64_t)z->res.in_bytes);
 	z->remaining -= (int64_t)z->res.in_bytes;
 	z->cread = (int64_t)z->res.in_bytes;

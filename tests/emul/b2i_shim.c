@@ -14,6 +14,11 @@
 
 #include "b200inflate.h"
 #include "oracle.h"
+#include <stdio.h>
+
+/* B2I_SHIM_STATS=1: report how many device calls / streams the plugins made */
+static long g_calls, g_streams;
+static void shim_report(void) { if (getenv("B2I_SHIM_STATS")) fprintf(stderr, "shim: %ld decode calls, %ld streams\n", g_calls, g_streams); }
 
 struct b2i_ctx { int dummy; };
 
@@ -40,6 +45,9 @@ int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes, const b2i_
     size_t n, void *host_out, size_t out_bytes, b2i_stream_result *results)
 {
 	(void)c;
+	if (g_calls++ == 0)
+		atexit(shim_report);
+	g_streams += (long)n;
 	_Static_assert(sizeof(orc_desc) == sizeof(b2i_stream_desc), "descriptor layouts differ");
 	_Static_assert(sizeof(orc_stream_result) == sizeof(b2i_stream_result), "result layouts differ");
 	return orc_decode_batch(host_in, in_bytes, (const orc_desc *)descs, n, host_out, out_bytes,

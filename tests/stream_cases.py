@@ -26,6 +26,27 @@ def archive(framing):
     return synth.make_zip(members, framing=framing)
 
 
+def many_small(framing):
+    """Hundreds of small entries: with sizes in the local headers the streaming reader decodes
+    the deflate entries that follow the current one in the same device pass."""
+    txt = synth.synth_text(400000, 29)
+    members = []
+    for i in range(400):
+        body = txt[i * 700:i * 700 + 200 + (i * 37) % 3000]
+        if i % 9 == 4:
+            members.append(synth.ZipMember("s%03d.bin" % i, body, method=0))
+        elif i == 77:
+            members.append(synth.ZipMember("badcrc%03d" % i, body, crc=12345))
+        elif i == 150:
+            members.append(synth.ZipMember("empty%03d" % i, b""))
+        elif i == 201:
+            comp = synth.deflate_raw(body, 6)
+            members.append(synth.ZipMember("cut%03d" % i, body, comp=comp[:len(comp) // 2]))
+        else:
+            members.append(synth.ZipMember("f%03d.txt" % i, body, level=1 + i % 9))
+    return synth.make_zip(members, framing=framing)
+
+
 def report(binary, blob, block, opt=None):
     with tempfile.NamedTemporaryFile(suffix=".zip", delete=False) as f:
         f.write(blob)
@@ -61,3 +82,8 @@ def check(ref_binary, new_binary):
                 a = comparable(report(ref_binary, blob, block, opt))
                 b = comparable(report(new_binary, blob, block, opt))
                 assert a == b, (framing, block, opt, len(blob), a, b)
+        z = many_small(framing)
+        for block in (4096, 1 << 24):
+            a = comparable(report(ref_binary, z, block))
+            b = comparable(report(new_binary, z, block))
+            assert a == b, (framing, block, [x for x, y in zip(a, b) if x != y][:3], [y for x, y in zip(a, b) if x != y][:3])
