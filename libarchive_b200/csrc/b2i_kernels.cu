@@ -63,7 +63,7 @@ b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *_
 		if (lane == 0) {
 			unsigned smid;
 			asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-			slot = (smid * INFLATE_SLOTS + (blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5)) % INFLATE_SLOTS) % nslots;
+			slot = (smid * INFLATE_SLOTS + (blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5)) % (2u * INFLATE_CTAS * INFLATE_WARPS)) % nslots;
 			while (atomicCAS(&slot_busy[slot], 0u, 1u) != 0u)
 				slot = slot + 1 == nslots ? 0 : slot + 1;
 		}
