@@ -7,7 +7,7 @@
  * archive_read_support_format_zip / _raw, archive_read_support_filter_gzip,
  * archive_read_open_memory, archive_read_next_header, archive_read_data_block.
  *
- *   oracle_extract list  <file> [--raw] [--opt zip:ignorecrc32] [--dump out.bin] [--stream BLOCK]
+ *   oracle_extract list  <file> [--raw] [--opt zip:ignorecrc32] [--dump out.bin] [--stream BLOCK] [--meta]
  *       one JSON line per entry: name, size, header/read return codes, bytes
  *       read, CRC-32 (zlib) of the bytes read, block sizes, error string
  *   oracle_extract bench <file> [--raw] --procs P [--reps R]
@@ -84,6 +84,7 @@ json_str(FILE *f, const char *s)
  * (no seek, no skip), so that the ZIP STREAMING reader is the one that runs */
 static struct { const unsigned char *p; size_t left, blk; } g_src;
 static int g_stream_blk;
+static int g_meta;      /* --meta: owner, access/change times, link target, encryption flags as well */
 
 static la_ssize_t
 stream_read(struct archive *a, void *cd, const void **buff)
@@ -179,6 +180,14 @@ cmd_list(const void *buf, size_t len, int raw, const char *opt, const char *dump
 		    (long long)archive_entry_size(e), archive_entry_size_is_set(e),
 		    (unsigned)archive_entry_mode(e), (long long)archive_entry_mtime(e), hr);
 		json_str(stdout, herr);
+		if (g_meta) {
+			printf(",\"uid\":%lld,\"gid\":%lld,\"atime\":%lld,\"ctime\":%lld,\"enc\":%d,\"menc\":%d,\"has_enc\":%d,\"link\":",
+			    (long long)archive_entry_uid(e), (long long)archive_entry_gid(e),
+			    (long long)archive_entry_atime(e), (long long)archive_entry_ctime(e),
+			    archive_entry_is_data_encrypted(e), archive_entry_is_metadata_encrypted(e),
+			    archive_read_has_encrypted_entries(a));
+			json_str(stdout, archive_entry_symlink(e));
+		}
 		printf(",\"format\":");
 		json_str(stdout, archive_format_name(a));
 		printf(",\"rd\":%d,\"nbytes\":%llu,\"crc\":\"%08lx\",\"nblk\":%d,\"blocks\":[",
@@ -373,6 +382,7 @@ main(int argc, char **argv)
 		else if (!strcmp(argv[i], "--reps") && i + 1 < argc) reps = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--limit") && i + 1 < argc) limit = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--stream") && i + 1 < argc) g_stream_blk = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--meta")) g_meta = 1;
 	}
 	buf = slurp(argv[2], &len);
 	if (!strcmp(argv[1], "list"))

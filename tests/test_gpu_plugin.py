@@ -142,3 +142,14 @@ def test_streaming_reader_identical_reports():
         pytest.skip("oracle/_ref not built")
     import stream_cases
     stream_cases.check(ob.REF_EXTRACT, DROPIN)
+
+
+def test_reference_fixtures_full_metadata_identical():
+    """All reference fixtures through the drop-in and the reference, seekable and streamed, with
+    owner, access / change times, link targets and encryption flags in the report."""
+    need_dropin()
+    if not ob.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import stream_cases
+    stream_cases.check_fixtures(ob.REF_EXTRACT, DROPIN, os.path.join(GOLD, "ref_fixtures"),
+                                {k: v["raw"] for k, v in EXPECTED.items()}, refused=tuple(REFUSED))

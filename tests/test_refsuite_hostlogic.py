@@ -53,3 +53,19 @@ def test_streaming_reader_reports_match_reference():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import stream_cases
     stream_cases.check(ref, new)
+
+
+def test_reference_fixtures_full_metadata_match_reference():
+    """All reference fixtures, seekable and streamed, including owner / access and change times /
+    link targets / encryption flags (the extra fields 0x5455, 0x5855, 0x7855, 0x7875, 0x7075)."""
+    import json
+    ref, new = os.path.join(REFDIR, "oracle_extract"), os.path.join(REFDIR, "hostlogic_extract")
+    if not (os.path.exists(ref) and os.path.exists(new)):
+        pytest.skip("oracle/_ref drivers not built (needs /root/reference)")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import stream_cases
+    gold = os.path.join(ROOT, "tests", "golden")
+    expected = json.load(open(os.path.join(gold, "ref_expected.json")))
+    stream_cases.check_fixtures(ref, new, os.path.join(gold, "ref_fixtures"), {k: v["raw"] for k, v in expected.items()},
+                                refused=("test_read_format_zip_encryption_data.zip",))
