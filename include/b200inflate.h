@@ -241,6 +241,18 @@ int  b2i_gzip_scan_bgzf(const void *buf, size_t size, size_t off,
                         b2i_gzip_member **members, size_t *n, size_t *end_off);
 void b2i_free(void *);
 
+/* ---- multi-GPU partition (host arithmetic, no GPU involved) ---------
+ * Streams are independent (inflateReset per entry, archive_read_support_format_zip.c:
+ * 2517-2518; inflateInit2 per member, archive_read_support_filter_gzip.c:363), so one
+ * archive is split across the GPUs of a box on the host and nothing is exchanged.
+ * contiguous: cuts[parts + 1], part p = descriptors [cuts[p], cuts[p+1]) in input
+ * order, about equal in_len + out bytes: one compressed range in, one output range
+ * out per GPU.  lpt: owner[i] = part of stream i, largest streams placed first on the
+ * least loaded part (batches dominated by a few huge entries); load[parts] optional. */
+int  b2i_partition_contiguous(const b2i_stream_desc *descs, size_t n, int parts, size_t *cuts);
+int  b2i_partition_lpt(const b2i_stream_desc *descs, size_t n, int parts, uint32_t *owner,
+                       uint64_t *load);
+
 #ifdef __cplusplus
 }
 #endif

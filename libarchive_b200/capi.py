@@ -60,7 +60,7 @@ EXPORTS = [
     "b2i_device_free", "b2i_memcpy_h2d", "b2i_memcpy_d2h", "b2i_plan_create", "b2i_plan_launch",
     "b2i_plan_results", "b2i_plan_destroy", "b2i_decode_host", "b2i_submit", "b2i_wait", "b2i_crc32", "b2i_crc32_device",
     "b2i_crc32_combine", "b2i_zip_index_build", "b2i_zip_index_free", "b2i_gzip_peek_header",
-    "b2i_gzip_scan_bgzf", "b2i_free",
+    "b2i_gzip_scan_bgzf", "b2i_free", "b2i_partition_contiguous", "b2i_partition_lpt",
 ]
 
 _lib = None
@@ -116,6 +116,8 @@ def lib():
                                      C.POINTER(sz)]
     L.b2i_free.argtypes = [vp]
     L.b2i_free.restype = None
+    L.b2i_partition_contiguous.argtypes = [C.POINTER(StreamDesc), sz, C.c_int, C.POINTER(sz)]
+    L.b2i_partition_lpt.argtypes = [C.POINTER(StreamDesc), sz, C.c_int, C.POINTER(u32), C.POINTER(u64)]
     _lib = L
     return L
 
@@ -233,3 +235,23 @@ def gzip_scan_bgzf(buf: bytes, off: int = 0):
     out = [{f: getattr(mem[i], f) for f, _ in GzipMember._fields_} for i in range(n.value)]
     L.b2i_free(mem)
     return out, end.value
+
+
+def partition_contiguous(descs, parts: int):
+    """b2i_partition_contiguous -> [(lo, hi)] * parts (descriptor index ranges)."""
+    cuts = (C.c_size_t * (parts + 1))()
+    rc = lib().b2i_partition_contiguous(descs, len(descs), parts, cuts)
+    if rc != OK:
+        raise B2IError(f"b2i_partition_contiguous: {rc}")
+    return [(int(cuts[i]), int(cuts[i + 1])) for i in range(parts)]
+
+
+def partition_lpt(descs, parts: int):
+    """b2i_partition_lpt -> (owner list, load list)."""
+    n = len(descs)
+    owner = (C.c_uint32 * max(n, 1))()
+    load = (C.c_uint64 * parts)()
+    rc = lib().b2i_partition_lpt(descs, n, parts, owner, load)
+    if rc != OK:
+        raise B2IError(f"b2i_partition_lpt: {rc}")
+    return [int(owner[i]) for i in range(n)], [int(x) for x in load]

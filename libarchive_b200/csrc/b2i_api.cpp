@@ -153,7 +153,8 @@ extern "C" int b2i_ctx_create(int device, void *cuda_stream, b2i_ctx **out)
 		}
 		c->own_stream = true;
 	}
-	if (cudaMalloc(&c->d_crc_tab, 1024 * 4) != cudaSuccess ||
+	if (b2i_kernels_configure() != cudaSuccess ||
+	    cudaMalloc(&c->d_crc_tab, 1024 * 4) != cudaSuccess ||
 	    cudaMalloc(&c->d_xp8, 40 * 4) != cudaSuccess ||
 	    cudaMalloc(&c->d_ztab, 1024 * 4) != cudaSuccess ||
 	    cudaMalloc(&c->d_lane_mul, 32 * 4) != cudaSuccess ||
@@ -325,8 +326,9 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 			e.nwork = (uint32_t)work.size() - e.first_work;
 			ents.push_back(e);
 			max_in = std::max<uint64_t>(max_in, d.in_off + d.in_len);
-			if (!(d.flags & B2I_F_NO_COPY))
-				max_out = std::max<uint64_t>(max_out, d.out_off + std::min(d.in_len, d.out_cap));
+			/* an entry larger than its reserved output is never copied (S_OUT_OVERFLOW) */
+			if (!(d.flags & B2I_F_NO_COPY) && d.in_len <= d.out_cap)
+				max_out = std::max<uint64_t>(max_out, d.out_off + d.in_len);
 		} else {
 			unsup.push_back((uint32_t)i);
 		}
@@ -335,19 +337,18 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 	std::stable_sort(deflate.begin(), deflate.end(), [&](uint32_t a, uint32_t b) {
 		return descs[a].in_len + descs[a].out_cap > descs[b].in_len + descs[b].out_cap;
 	});
-	/* Experimental, off by default (B2I_TEAM_MIN_BYTES=<bytes> turns it on): streams
-	 * with at least this much input get a whole CTA (inflate_team.cuh).  Measured on
-	 * B200 with 8 MiB streams: 1.15-1.18x only - decoding scales with the warps, but
-	 * resolving matches is a dependency chain through recent output, so the warps
-	 * of a team wait for each other. */
-	uint64_t team_min = 0;
+	/* Streams that move at least B2I_TEAM_MIN_BYTES (compressed + uncompressed, default
+	 * 1 MiB; 0 = never) get a whole CTA each (inflate_team.cuh): a lone warp decodes one
+	 * stream at a few tens of MB/s, a CTA with its window in shared memory an order of
+	 * magnitude faster, which is what bounds batches with multi-megabyte entries. */
+	uint64_t team_min = 1u << 20;
 	if (const char *ev = getenv("B2I_TEAM_MIN_BYTES"))
 		team_min = strtoull(ev, NULL, 10);
 	std::vector<uint32_t> big;
 	if (team_min != 0) {
 		std::vector<uint32_t> small;
 		for (uint32_t i : deflate)
-			(descs[i].in_len >= team_min ? big : small).push_back(i);
+			(descs[i].in_len + descs[i].out_cap >= team_min ? big : small).push_back(i);
 		deflate.swap(small);
 	}
 
@@ -454,15 +455,12 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 		return fail(c, B2I_E_INVAL, "d_out must be 16-byte aligned");
 	CU(c, cudaSetDevice(c->device));
 	if (p->n_big) {
-		/* fork: the team kernel (few, long CTAs) runs on its own stream next to everything else */
+		/* fork: the team kernel (one CTA per large stream) runs on its own stream next to
+		 * everything else; the single-warp kernel is launched first so that the short
+		 * streams occupy the SMs while they last and the team CTAs fill in behind them */
 		CU(c, cudaMemsetAsync(p->d_counter, 0, 8, p->stream));
 		CU(c, cudaEventRecord(p->ev_fork, p->stream));
 		CU(c, cudaStreamWaitEvent(c->s_team, p->ev_fork, 0));
-		CU(c, b2i_launch_inflate_team((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out, p->out_mirror, p->d_descs,
-		    p->d_results, p->d_order + p->n_deflate, p->n_big, p->d_counter + 1, c->d_crc_tab, c->d_xp8,
-		    c->d_scratch, c->d_slot_busy, c->num_sms, c->s_team));
-		CU(c, cudaEventRecord(p->ev_join, c->s_team));
-		c->launches++;
 	}
 	if (p->n_deflate) {
 		if (!p->n_big)
@@ -477,6 +475,13 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 		CU(c, (r9 ? b2i_launch_inflate_r9 : b2i_launch_inflate)((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out,
 		    p->out_mirror, p->d_descs, p->d_results, p->d_order, p->n_deflate, p->d_counter, c->d_crc_tab, c->d_xp8,
 		    getenv("B2I_UNIFORM_ONLY") ? NULL : c->d_scratch, c->d_slot_busy, c->num_sms, p->stream));
+		c->launches++;
+	}
+	if (p->n_big) {
+		CU(c, b2i_launch_inflate_team((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out, p->out_mirror, p->d_descs,
+		    p->d_results, p->d_order + p->n_deflate, p->n_big, p->d_counter + 1, c->d_crc_tab, c->d_xp8,
+		    c->d_scratch, c->d_slot_busy, c->num_sms, c->s_team));
+		CU(c, cudaEventRecord(p->ev_join, c->s_team));
 		c->launches++;
 	}
 	if (p->n_stored) {

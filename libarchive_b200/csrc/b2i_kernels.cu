@@ -96,7 +96,7 @@ b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *_
  * Warp 0 pulls streams from the counter and owns them; the other warps serve its
  * PASS / RESOLVE commands until it quits.
  */
-extern "C" __global__ void __launch_bounds__(TEAM_LANES, 4)
+extern "C" __global__ void __launch_bounds__(TEAM_LANES, 2)
 b2i_inflate_team_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *__restrict__ out,
     uint8_t *__restrict__ out_mirror,
     const B2iDesc *__restrict__ descs, B2iResult *__restrict__ results,
@@ -107,8 +107,8 @@ b2i_inflate_team_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const unsigned w = threadIdx.x >> 5;
 	const unsigned lane = threadIdx.x & 31;
-	WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + w;
-	TeamShared *ts = reinterpret_cast<TeamShared *>(smem_raw + sizeof(WarpSmem) * TEAM_WARPS);
+	TeamShared *ts = reinterpret_cast<TeamShared *>(smem_raw);
+	WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw + sizeof(TeamShared));   /* warp 0's tables */
 	uint32_t slot = 0;
 
 	if (lane == 0) {
@@ -139,7 +139,7 @@ b2i_inflate_team_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8
 		}
 		team_command(ts, TC_QUIT);
 	} else {
-		team_serve(ts, w, sm);
+		team_serve(ts, w);
 	}
 	if (lane == 0) {
 		__threadfence();
@@ -241,7 +241,9 @@ b2i_crc_chunks_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
 		}
 		if (lane == 0)
 			partial[w] = raw0;
-		if (!(d.flags & F_NO_COPY)) {
+		/* an entry that does not fit its reserved output is not copied at all: the
+		 * combine kernel reports S_OUT_OVERFLOW for it and nobody else's bytes are touched */
+		if (!(d.flags & F_NO_COPY) && d.in_len <= d.out_cap) {
 			uint8_t *dst = out + d.out_off + k.rel;
 			if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
 				const uint4 *s4 = (const uint4 *)src;
@@ -368,24 +370,47 @@ cudaError_t b2i_launch_tables(uint32_t *crc_tab, uint32_t *xp8, uint32_t *ztab, 
 
 #endif /* !B2I_R9 */
 
+/* Function attributes are per device: b2i_ctx_create calls this with the context's
+ * device current (not a process-wide flag: a second GPU needs its own settings). */
+#ifdef B2I_R9
+cudaError_t b2i_kernels_configure_r9(void)
+#else
+cudaError_t b2i_kernels_configure_r9(void);
+cudaError_t b2i_kernels_configure(void)
+#endif
+{
+	cudaError_t e = cudaFuncSetAttribute(b2i_inflate_kernel,
+	    cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (e != cudaSuccess)
+		return e;
+	e = cudaFuncSetAttribute(b2i_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)(sizeof(WarpSmem) * INFLATE_WARPS));
+	if (e != cudaSuccess)
+		return e;
+#ifndef B2I_R9
+	e = cudaFuncSetAttribute(b2i_inflate_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)(sizeof(WarpSmem) + sizeof(TeamShared)));
+	if (e != cudaSuccess)
+		return e;
+	e = cudaFuncSetAttribute(b2i_inflate_team_kernel,
+	    cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (e != cudaSuccess)
+		return e;
+	e = cudaFuncSetAttribute(b2i_crc_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)(ZREP_WORDS * sizeof(uint32_t)));
+	if (e != cudaSuccess)
+		return e;
+	e = b2i_kernels_configure_r9();
+#endif
+	return e;
+}
+
 cudaError_t b2i_launch_inflate(const uint8_t *in, uint64_t in_total, uint8_t *out, uint8_t *out_mirror,
     const B2iDesc *descs, B2iResult *results, const uint32_t *order, uint32_t n,
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
     unsigned int *slot_busy, int num_sms, cudaStream_t st)
 {
-	static bool configured = false;
 	const size_t smem = sizeof(WarpSmem) * INFLATE_WARPS;
-	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(b2i_inflate_kernel,
-		    cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		if (e != cudaSuccess)
-			return e;
-		e = cudaFuncSetAttribute(b2i_inflate_kernel,
-		    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess)
-			return e;
-		configured = true;
-	}
 	uint32_t blocks = (n + INFLATE_WARPS - 1) / INFLATE_WARPS;
 	uint32_t max_blocks = (uint32_t)num_sms * INFLATE_CTAS;
 	if (blocks > max_blocks)
@@ -401,15 +426,7 @@ cudaError_t b2i_launch_inflate_team(const uint8_t *in, uint64_t in_total, uint8_
     unsigned int *counter, const uint32_t *crc_tab, const uint32_t *xp8, uint32_t *scratch,
     unsigned int *slot_busy, int num_sms, cudaStream_t st)
 {
-	static bool configured = false;
-	const size_t smem = sizeof(WarpSmem) * TEAM_WARPS + sizeof(TeamShared);
-	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(b2i_inflate_team_kernel,
-		    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess)
-			return e;
-		configured = true;
-	}
+	const size_t smem = sizeof(WarpSmem) + sizeof(TeamShared);
 	uint32_t blocks = n < (uint32_t)num_sms * 2u ? n : (uint32_t)num_sms * 2u;
 	b2i_inflate_team_kernel<<<blocks, TEAM_LANES, smem, st>>>(in, in_total, out, out_mirror, descs,
 	    results, order, n, counter, crc_tab, xp8, scratch, slot_busy, b2i_inflate_scratch_slots(num_sms));
@@ -420,15 +437,7 @@ cudaError_t b2i_launch_crc_chunks(const uint8_t *in, uint8_t *out, const B2iDesc
     const B2iCrcWork *work, uint32_t nwork, uint32_t *partial, const uint32_t *crc_tab,
     const uint32_t *xp8, const uint32_t *ztab, const uint32_t *lane_mul, int num_sms, cudaStream_t st)
 {
-	static bool configured = false;
 	const size_t smem = ZREP_WORDS * sizeof(uint32_t);
-	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(b2i_crc_chunks_kernel,
-		    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess)
-			return e;
-		configured = true;
-	}
 	uint32_t blocks = (nwork + 31) / 32;
 	if (blocks > (uint32_t)num_sms)
 		blocks = (uint32_t)num_sms;

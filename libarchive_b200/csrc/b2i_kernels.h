@@ -18,6 +18,8 @@ struct B2iCrcEntry {
 };
 #define B2I_CRC_CHUNK (32u * 1024u)   /* streaming pieces: 16-byte aligned, multiples of 512 bytes */
 
+/* per-device function attributes (dynamic shared memory sizes, carveout) */
+cudaError_t b2i_kernels_configure(void);
 size_t b2i_inflate_smem_bytes(void);
 size_t b2i_inflate_scratch_bytes(int num_sms);
 uint32_t b2i_inflate_scratch_slots(int num_sms);

@@ -575,21 +575,6 @@ B2I_DEV int decode_batch(WarpSmem *sm, Ring &r, Bits &b, uint32_t &my, uint32_t 
 #ifdef B2I_HOST_EMUL
 extern long g_stat_hist[64], g_stat_instage, g_stat_overlap, g_stat_batches, g_stat_bytes, g_stat_syms;
 #endif
-/*
- * Several warps resolving consecutive token ranges of ONE stream at the same time
- * (inflate_team.cuh).  Warp w owns output [range_start[w], range_end[w]); it may
- * gather from an earlier warp's range only below that warp's published flush
- * position, and the 16-byte unit it shares with its predecessor's tail is written
- * bytewise (head_skip = bytes of that unit that are not ours).
- */
-struct TeamLink {
-	volatile uint32_t *done_pos;      /* [nwarps] absolute output position flushed so far */
-	const uint32_t *range_start;      /* [nwarps] */
-	const uint32_t *range_end;        /* [nwarps] */
-	uint32_t w;                       /* this warp */
-	uint32_t head_skip;               /* leading foreign bytes of our first 16-byte unit */
-};
-
 #ifndef B2I_HOST_EMUL
 B2I_DEV uint8_t load_fresh(const uint8_t *p) { return __ldcg(p); }   /* L2: other warps' stores */
 B2I_DEV void fence_block() { __threadfence_block(); }
@@ -598,9 +583,8 @@ B2I_DEV uint8_t load_fresh(const uint8_t *p) { return *(volatile const uint8_t *
 B2I_DEV void fence_block() { __sync_synchronize(); }
 #endif
 
-template <bool TEAM>
-B2I_DEV uint32_t resolve_batch_t(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_t cap, uint32_t &outp, uint32_t &carry,
-    uint32_t my, uint32_t n, int32_t &stop, uint32_t &stop_detail, TeamLink *tl)
+B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_t cap, uint32_t &outp, uint32_t &carry,
+    uint32_t my, uint32_t n, int32_t &stop, uint32_t &stop_detail)
 {
 	const unsigned lane = b2i_lane();
 	uint32_t len = lane < n ? my >> 16 : 0;
@@ -664,35 +648,11 @@ B2I_DEV uint32_t resolve_batch_t(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint3
 			sm->wp[lane] = (uint8_t)(inc - pc);
 	}
 	__syncwarp();
-	if (TEAM) {
-		/* sources that lie in an earlier warp's range of this round must have been
-		 * flushed by that warp: wait for its published position */
-		const uint32_t own = tl->range_start[tl->w];
-		uint32_t hi = 0;
-		if (len >= 3) {
-			uint32_t send = outp + rel - val + (len < val ? len : val);   /* end of the source span */
-			hi = send < own ? send : own;
-			if (outp + rel - val >= own)
-				hi = 0;
-		}
-		for (int o = 16; o; o >>= 1) {
-			uint32_t t = __shfl_xor_sync(B2I_FULL, hi, o);
-			hi = t > hi ? t : hi;
-		}
-		for (uint32_t v = tl->w; v-- > 0;) {
-			uint32_t req = hi < tl->range_end[v] ? hi : tl->range_end[v];
-			if (req <= tl->range_start[v])
-				continue;
-			while (tl->done_pos[v] < req)
-				;
-		}
-		fence_block();
-	}
 	/* round 1, one output byte per lane: a literal is stored as is, a match byte
 	 * whose source was flushed to global memory before this batch is fetched
 	 * (four loads in flight per lane); sources inside the staging buffer wait
 	 * for round 2. */
-	const int hs = TEAM ? (int)tl->head_skip : 0;
+	const int hs = 0;
 	for (uint32_t t0 = 0; t0 < T; t0 += 128) {
 		uint32_t v[4];
 		bool st[4];
@@ -714,12 +674,10 @@ B2I_DEV uint32_t resolve_batch_t(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint3
 				if (oval < olen)
 					off %= oval;               /* overlapping copy: period = distance */
 				int sidx = (int)(c + ro + off) - (int)oval;
-				/* team: the first hs bytes of the staging buffer stand for the previous
-				 * warp's tail, which lives in global memory, not here */
 				st[k] = sidx < hs;
 				B2I_CHECK(sidx >= -(int)(outp - c) && sidx < (int)STAGE_BYTES);
 				if (sidx < hs)
-					v[k] = TEAM ? load_fresh(g16 + sidx) : g16[sidx];
+					v[k] = g16[sidx];
 			}
 		}
 #pragma unroll
@@ -757,38 +715,17 @@ B2I_DEV uint32_t resolve_batch_t(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint3
 		for (uint32_t g = lane; g < 64; g += 32) {
 			if (g < groups) {
 				const uint4 v16 = *(const uint4 *)(stg + 16 * g);
-				if (TEAM && g == 0 && tl->head_skip) {
-					/* shared with the previous warp's tail: only our bytes */
-					for (uint32_t i = tl->head_skip; i < 16; i++) {
-						g16[i] = stg[i];
-						if (mir) mir[(outp - c) + i] = stg[i];
-					}
-				} else {
-					*(uint4 *)(g16 + 16 * g) = v16;
-					if (mir)            /* host-mapped copy of the output (B2I_MIRROR) */
-						*(uint4 *)(mir + (outp - c) + 16 * g) = v16;
-				}
+				*(uint4 *)(g16 + 16 * g) = v16;
+				if (mir)            /* host-mapped copy of the output (B2I_MIRROR) */
+					*(uint4 *)(mir + (outp - c) + 16 * g) = v16;
 			}
 		}
 		if (lane < (fill & 15u))
 			carry = stg[16 * groups + lane];
 		__syncwarp();
-		if (TEAM) {
-			if (groups)
-				tl->head_skip = 0;
-			fence_block();
-			if (lane == 0)
-				tl->done_pos[tl->w] = (outp - c) + 16 * groups;
-		}
 	}
 	outp += T;
 	return taken;
-}
-
-B2I_DEV uint32_t resolve_batch(WarpSmem *sm, uint8_t *out, uint8_t *mir, uint32_t cap, uint32_t &outp, uint32_t &carry,
-    uint32_t my, uint32_t n, int32_t &stop, uint32_t &stop_detail)
-{
-	return resolve_batch_t<false>(sm, out, mir, cap, outp, carry, my, n, stop, stop_detail, nullptr);
 }
 
 #include "inflate_lp.cuh"
@@ -829,6 +766,8 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, TeamS
 	r.next_issue = 0;
 	b.rd_end = lead + (uint32_t)in_len;
 	bits_seek(sm, r, b, lead);
+	if (team)
+		team_stream_begin(team);
 	PH_DECL();
 
 	do {
@@ -864,15 +803,22 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, TeamS
 				out[(outp & ~15u) + lane] = (uint8_t)carry;
 				if (mir) mir[(outp & ~15u) + lane] = (uint8_t)carry;
 			}
-			for (uint32_t i = lane; i < ncopy; i += 32) {
-				const uint8_t v8 = src[i];
-				dst[i] = v8;
-				if (mir) mir[outp + i] = v8;
+			if (team && ncopy >= 4096u) {
+				__syncwarp();
+				fence_block();
+				team_copy_stored(team, src, dst, ncopy);
+				fence_block();
+			} else {
+				for (uint32_t i = lane; i < ncopy; i += 32) {
+					const uint8_t v8 = src[i];
+					dst[i] = v8;
+					if (mir) mir[outp + i] = v8;
+				}
 			}
 			__syncwarp();
 			outp += ncopy;
 			if (lane < (outp & 15u))
-				carry = out[(outp & ~15u) + lane];
+				carry = load_fresh(out + (outp & ~15u) + lane);
 			bits_seek(sm, r, b, pos + ncopy);
 			if (ncopy < len) {
 				b.over = 1 << 20;  /* input ran out inside the block */

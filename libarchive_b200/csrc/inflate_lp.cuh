@@ -95,7 +95,15 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 		LP_LOAD();
 		LP_DROP(start & 31u);
 	}
+#ifdef B2I_EMUL_TRACE
+	unsigned long iters_ = 0;
+#endif
 	while (__any_sync(B2I_FULL, active)) {
+#ifdef B2I_EMUL_TRACE
+		if (++iters_ == 3000 && active)
+			fprintf(stderr, "lp_pass stuck: lane %u start %u widx %u cnt %d ns %u stop_at %u hard_end %u wbase %u max_word %u\n",
+			    b2i_lane(), start, widx, cnt, ns, stop_at, hard_end, wbase, max_word);
+#endif
 		if (!active)
 			continue;
 		if (cnt <= 30)

@@ -21,9 +21,17 @@ B2I_DEV void process_deflate_stream(WarpSmem *sm, Ring &ring, uint32_t *scratch,
 
 	PH_DECL();
 	if (so.status == S_OK && !(d.flags & F_NO_CRC)) {
-		/* the lit/len table is dead now: its space holds the slice tables */
-		crc_load_tables(sm->lit, crc_tab_g);
-		uint32_t raw0 = crc_warp_raw0(out + d.out_off, so.out_bytes, sm->lit, xp8);
+		uint32_t raw0;
+		if (team && so.out_bytes >= 65536u) {
+			/* a large stream: every warp of the team takes a slice */
+			__syncwarp();
+			fence_block();
+			raw0 = team_crc_raw0(team, out + d.out_off, so.out_bytes, crc_tab_g, xp8);
+		} else {
+			/* the lit/len table is dead now: its space holds the slice tables */
+			crc_load_tables(sm->lit, crc_tab_g);
+			raw0 = crc_warp_raw0(out + d.out_off, so.out_bytes, sm->lit, xp8);
+		}
 		crc = crc_finish(0, raw0, so.out_bytes, xp8);
 		__syncwarp();
 	}

@@ -263,13 +263,19 @@ def config4_sizes(total: int = 8 << 30, lo: int = 1 << 10, hi: int = 16 << 20, s
     return sizes
 
 
-def config4_zip64_mixed(total: int = 8 << 30, lo: int = 1 << 10, hi: int = 16 << 20, seed: int = 4) -> bytes:
-    sizes = config4_sizes(total, lo, hi, seed)
+def config4_zip64_mixed(total: int = 8 << 30, lo: int = 1 << 10, hi: int = 16 << 20, seed: int = 4,
+                        force=(), threads: int = 8) -> bytes:
+    """BASELINE config 4.  `force` = extra (size, kind) entries put in front of the
+    log-uniform ones (kind 0 dynamic, 3 fixed, 6 stored blocks, 9 interleaved), so that a
+    scaled-down archive still holds entries of the maximum size."""
+    sizes = [int(s) for s, _ in force] + config4_sizes(total, lo, hi, seed)
     rng = np.random.default_rng(seed + 1)
     text = synth_text(min(max(sizes) + (1 << 20), 64 << 20), seed)
     members = []
     for i, s in enumerate(sizes):
         kind = int(rng.integers(0, 10))
+        if i < len(force):
+            kind = int(force[i][1])
         o = int(rng.integers(0, max(1, len(text) - s))) if s <= len(text) else 0
         payload = (text * (s // len(text) + 1))[o:o + s] if s > len(text) - o else text[o:o + s]
         if kind < 3:      # dynamic Huffman
@@ -285,7 +291,7 @@ def config4_zip64_mixed(total: int = 8 << 30, lo: int = 1 << 10, hi: int = 16 <<
                                   (payload[b:], 1, zlib.Z_FIXED)])
             data = payload[:a] + synth_random(b - a, seed + i) + payload[b:]
             members.append(ZipMember("m%05d.mix" % i, data, comp=comp))
-    return make_zip(members, zip64=True)
+    return make_zip(members, zip64=True, threads=threads)
 
 
 def config5_zip64_tiny(n_entries: int = 500_000, entry: int = 4096, seed: int = 5) -> bytes:

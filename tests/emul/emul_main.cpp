@@ -107,7 +107,7 @@ extern "C" uint32_t emul_crc32(uint32_t crc, const uint8_t *buf, uint64_t off, u
 /* ---- a team of TEAM_WARPS warps on one stream (inflate_team.cuh) ---------------- */
 struct TeamJob {
 	EmulWarp warp[TEAM_WARPS];
-	WarpSmem sm[TEAM_WARPS];
+	WarpSmem sm[1];
 	TeamShared ts;
 	pthread_barrier_t bar;
 	uint32_t *scratch[TEAM_WARPS];
@@ -133,7 +133,7 @@ static void *team_lane_main(void *p)
 		    j->d, &j->res, g_crc_tab, g_xp8);
 		team_command(&j->ts, TC_QUIT);
 	} else {
-		team_serve(&j->ts, a->w, &j->sm[a->w]);
+		team_serve(&j->ts, a->w);
 	}
 	return NULL;
 }

@@ -18,6 +18,7 @@
 #define __align__(n) __attribute__((aligned(n)))
 
 struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
 
 struct EmulWarp {
 	pthread_barrier_t bar;

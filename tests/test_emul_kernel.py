@@ -101,10 +101,13 @@ def test_stored_block_resume_at_every_ring_phase():
     check("mixed", s, cap=1 << 14, leads=range(0, 128))
 
 
-def test_team_decoder_small_cases():
-    """inflate_team.cuh under the emulator (4 warps = 128 pthreads, slow: tiny inputs):
-    shared tables, 128-segment rounds, concurrent resolution with flush watermarks."""
-    txt = synth.synth_text(14000, 23)
+def test_team_decoder_cases():
+    """inflate_team.cuh under the emulator (8 warps = 256 pthreads): shared tables,
+    256-segment rounds, tokens -> bytes through the shared-memory chunk buffer (expand,
+    pointer sweep, flush + history ring), stored blocks copied by the team, team CRC,
+    partial regions (one segment larger than the chunk), capacity and distance errors cut
+    at the exact symbol."""
+    txt = synth.synth_text(300000, 23)
 
     def team(s, cap, lead):
         buf = bytes(lead) + s
@@ -117,13 +120,32 @@ def test_team_decoder_small_cases():
         return r, out.raw[:r.out_bytes]
 
     full = synth.deflate_raw(txt, 6)
-    for name, s, cap in [("text", full, 1 << 15), ("truncated", full[:3000], 1 << 15), ("cap", full, 6000),
-                         ("fixed", synth.deflate_raw(txt[:7000], 6, zlib.Z_FIXED), 1 << 15)]:
+    dic = synth.synth_text(30000, 77)
+    far_body = synth.synth_text(20000, 78) + dic[25000:] + synth.synth_text(9000, 79)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY, dic)
+    far = synth.deflate_raw(txt[:2000], 6)      # placeholder replaced below
+    c1 = zlib.compressobj(6, zlib.DEFLATED, -15)
+    far = c1.compress(txt[:2000]) + c1.flush(zlib.Z_FULL_FLUSH) + co.compress(far_body) + co.flush()
+    mixed = synth.deflate_mixed([(txt[:100000], 6, zlib.Z_DEFAULT_STRATEGY),
+                                 (synth.synth_random(70000, 3), 6, zlib.Z_DEFAULT_STRATEGY),
+                                 (txt[100000:200000], 1, zlib.Z_FIXED)])
+    cases = [("text", full, 1 << 19, 9), ("small", synth.deflate_raw(txt[:14000], 6), 1 << 15, 3),
+             ("truncated", full[:50000], 1 << 19, 0), ("cap", full, 123457, 5),
+             ("fixed", synth.deflate_raw(txt[:200000], 1, zlib.Z_FIXED), 1 << 18, 1),
+             ("stored-blocks", synth.deflate_raw(synth.synth_random(200000, 5), 6), 1 << 18, 7),
+             ("mixed", mixed, 1 << 19, 11),
+             ("rle", synth.deflate_raw((b"ab" * 50000 + txt[:5000]) * 6, 6), 1 << 20, 2),
+             ("zeros", synth.deflate_raw(bytes(8 << 20), 6), 9 << 20, 13),
+             ("zeros-cap", synth.deflate_raw(bytes(8 << 20), 6), (8 << 20) - 100001, 13),
+             ("far-mid-stream", far, 1 << 17, 4)]
+    for name, s, cap, lead in cases:
         o, od = ob.inflate(s, cap)
-        r, ed = team(s, cap, 9)
-        assert r.status == o.status and ed == od, (name, r.status, o.status)
+        r, ed = team(s, cap, lead)
+        assert r.status == o.status and r.out_bytes == o.out_bytes and ed == od, (name, r.status, o.status, r.out_bytes, o.out_bytes)
         if o.status == 0:
             assert r.in_bytes == o.in_bytes and r.crc == (zlib.crc32(od) & 0xFFFFFFFF), name
+        if name == "far-mid-stream":
+            assert o.status == -3 and 2000 < o.out_bytes < 30000 and r.detail == 11
 
 
 def test_nine_bit_root_build(monkeypatch):
