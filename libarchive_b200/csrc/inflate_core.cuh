@@ -767,7 +767,7 @@ B2I_DEV StreamOut inflate_stream(WarpSmem *sm, Ring &r, uint32_t *scratch, TeamS
 	b.rd_end = lead + (uint32_t)in_len;
 	bits_seek(sm, r, b, lead);
 	if (team)
-		team_stream_begin(team);
+		team_stream_begin(team, out, mir, cap);
 	PH_DECL();
 
 	do {

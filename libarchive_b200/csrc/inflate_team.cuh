@@ -332,7 +332,7 @@ B2I_DEV void team_crc(TeamShared *ts, unsigned w)
 		tab[i] = ts->crc_tab_g[i];
 	team_sync();
 	const uint64_t n = ts->crc_n;
-	const uint64_t slice = ((n / TEAM_WARPS) + 15) & ~(uint64_t)15;
+	const uint64_t slice = (((n + TEAM_WARPS - 1) / TEAM_WARPS) + 15) & ~(uint64_t)15;     /* 8 slices cover n */
 	const uint64_t lo = (uint64_t)w * slice < n ? (uint64_t)w * slice : n;
 	const uint64_t hi = lo + slice < n ? lo + slice : n;
 	uint32_t raw0 = crc_warp_raw0(ts->crc_p + lo, hi - lo, tab, ts->crc_xp8);
@@ -422,11 +422,14 @@ B2I_DEV uint32_t team_crc_raw0(TeamShared *ts, const uint8_t *p, uint64_t n, con
 }
 
 /* once per stream (warp 0) */
-B2I_DEV void team_stream_begin(TeamShared *ts)
+B2I_DEV void team_stream_begin(TeamShared *ts, uint8_t *out, uint8_t *mir, uint32_t cap)
 {
 	if (b2i_lane() == 0) {
 		ts->hist_pos = TEAM_NOERR;
 		ts->next_seg = TEAM_SEG_INIT;
+		ts->out = out;
+		ts->mir = mir;
+		ts->cap = cap;
 	}
 	__syncwarp();
 }

@@ -133,6 +133,8 @@ def test_team_decoder_cases():
              ("truncated", full[:50000], 1 << 19, 0), ("cap", full, 123457, 5),
              ("fixed", synth.deflate_raw(txt[:200000], 1, zlib.Z_FIXED), 1 << 18, 1),
              ("stored-blocks", synth.deflate_raw(synth.synth_random(200000, 5), 6), 1 << 18, 7),
+             # n = 8 * 16 * k + 3: the eight CRC slices must still cover the last bytes
+             ("crc-slices", synth.deflate_raw(synth.synth_random(8 * 16 * 600 + 3, 6), 6), 1 << 17, 6),
              ("mixed", mixed, 1 << 19, 11),
              ("rle", synth.deflate_raw((b"ab" * 50000 + txt[:5000]) * 6, 6), 1 << 20, 2),
              ("zeros", synth.deflate_raw(bytes(8 << 20), 6), 9 << 20, 13),
