@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B2I_ABI_VERSION 3
+#define B2I_ABI_VERSION 4
 
 /* ---- return codes of the API functions -------------------------------- */
 #define B2I_OK            0
@@ -167,6 +167,50 @@ int  b2i_submit(b2i_ctx *, const void *host_in, size_t in_bytes,
                 const b2i_stream_desc *descs, size_t n,
                 void *host_out, size_t out_bytes, b2i_job **job);
 int  b2i_wait(b2i_job *job, b2i_stream_result *res /* n entries */);
+
+/* The same over several GPUs of one box: the batch is partitioned on the
+ * host (b2i_partition_contiguous, or b2i_partition_lpt when a few streams dominate),
+ * every context decodes its share on its own thread with its own streams and pinned
+ * copies, nothing is exchanged between the devices.  One context per device is the
+ * intended use (several on one device also work); host_in / host_out should be pinned. */
+int  b2i_decode_host_multi(b2i_ctx *const *ctxs, int nctx, const void *host_in, size_t in_bytes,
+                           const b2i_stream_desc *descs, size_t n,
+                           void *host_out, size_t out_bytes, b2i_stream_result *res);
+
+/* ---- streaming pipeline: bounded memory, file-backed sources, all GPUs ----------
+ * Replaces the reference's serial "one block of the source, one inflate() call"
+ * loop (archive_read_open_filename.c:389-461 feeding
+ * archive_read_support_format_zip.c:2535-2690 / archive_read_support_filter_gzip.c:
+ * 431-511) for a whole archive: the descriptors (in_off = offset in the SOURCE,
+ * out_off ignored, archive order) are cut into windows of bounded output; windows are
+ * staged through a ring of pinned buffers, decoded round-robin by the given contexts
+ * (one worker thread and two jobs in flight per GPU) and handed out in order.
+ * Resident memory is windows_per_device x nctx x (window input + output), whatever
+ * the archive size.  Source: `mem` (the archive image in host memory: staged by copy
+ * threads, or used in place when it is pinned) or `fill` (called ONLY on the thread
+ * that calls b2i_pipe_get, so it may use libarchive's read filters: reads
+ * [offset, offset + len) of the source into dst, returns B2I_OK or an error). */
+typedef int (*b2i_fill_fn)(void *user, uint64_t offset, uint64_t len, void *dst);
+typedef struct b2i_pipe b2i_pipe;
+typedef struct b2i_pipe_opts {
+	size_t window_out_bytes;        /* 0: 64 MiB */
+	size_t first_window_out_bytes;  /* 0: a quarter of that (first bytes arrive sooner) */
+	int    windows_per_device;      /* ring depth, 0: 3 */
+	int    copy_threads;            /* staging threads for pageable memory, 0: 3 */
+} b2i_pipe_opts;
+int  b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, uint64_t mem_size,
+                   b2i_fill_fn fill, void *user, const b2i_stream_desc *descs, size_t n,
+                   const b2i_pipe_opts *opts, b2i_pipe **out);
+/* Blocks until stream idx is decoded.  *out_data: its bytes (NULL for B2I_F_NO_COPY
+ * stored streams), *in_data: its compressed bytes as staged; both stay valid until
+ * b2i_pipe_release moves past idx.  Asking for a stream in a later window drops the
+ * windows in between that have not been started (read_data_skip). */
+int  b2i_pipe_get(b2i_pipe *, size_t idx, const void **out_data, const void **in_data,
+                  b2i_stream_result *res);
+void b2i_pipe_release(b2i_pipe *, size_t idx);    /* streams < idx are done with */
+size_t b2i_pipe_window_count(const b2i_pipe *);
+const char *b2i_pipe_error(const b2i_pipe *);
+void b2i_pipe_close(b2i_pipe *);
 
 /* ---- scalar drop-ins --------------------------------------------------------
  * b2i_crc32: same contract as zlib crc32()/archive_crc32.h:43-84:

@@ -54,6 +54,13 @@ class GzipMember(C.Structure):
                 ("name_offset", C.c_uint32)]
 
 
+class PipeOpts(C.Structure):
+    _fields_ = [("window_out_bytes", C.c_size_t), ("first_window_out_bytes", C.c_size_t),
+                ("windows_per_device", C.c_int), ("copy_threads", C.c_int)]
+
+
+FILL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p)
+
 EXPORTS = [
     "b2i_ctx_create", "b2i_ctx_destroy", "b2i_last_error", "b2i_abi_version", "b2i_device_count",
     "b2i_ctx_sync", "b2i_ctx_launch_count", "b2i_host_alloc", "b2i_host_free", "b2i_device_alloc",
@@ -61,6 +68,8 @@ EXPORTS = [
     "b2i_plan_results", "b2i_plan_destroy", "b2i_decode_host", "b2i_submit", "b2i_wait", "b2i_crc32", "b2i_crc32_device",
     "b2i_crc32_combine", "b2i_zip_index_build", "b2i_zip_index_free", "b2i_gzip_peek_header",
     "b2i_gzip_scan_bgzf", "b2i_free", "b2i_partition_contiguous", "b2i_partition_lpt",
+    "b2i_decode_host_multi", "b2i_pipe_open", "b2i_pipe_get", "b2i_pipe_release", "b2i_pipe_window_count",
+    "b2i_pipe_error", "b2i_pipe_close",
 ]
 
 _lib = None
@@ -118,6 +127,19 @@ def lib():
     L.b2i_free.restype = None
     L.b2i_partition_contiguous.argtypes = [C.POINTER(StreamDesc), sz, C.c_int, C.POINTER(sz)]
     L.b2i_partition_lpt.argtypes = [C.POINTER(StreamDesc), sz, C.c_int, C.POINTER(u32), C.POINTER(u64)]
+    L.b2i_decode_host_multi.argtypes = [C.POINTER(vp), C.c_int, vp, sz, C.POINTER(StreamDesc), sz, vp, sz,
+                                        C.POINTER(StreamResult)]
+    L.b2i_pipe_open.argtypes = [C.POINTER(vp), C.c_int, vp, u64, FILL_FN, vp, C.POINTER(StreamDesc), sz,
+                                C.POINTER(PipeOpts), C.POINTER(vp)]
+    L.b2i_pipe_get.argtypes = [vp, sz, C.POINTER(vp), C.POINTER(vp), C.POINTER(StreamResult)]
+    L.b2i_pipe_release.argtypes = [vp, sz]
+    L.b2i_pipe_release.restype = None
+    L.b2i_pipe_window_count.argtypes = [vp]
+    L.b2i_pipe_window_count.restype = sz
+    L.b2i_pipe_error.argtypes = [vp]
+    L.b2i_pipe_error.restype = C.c_char_p
+    L.b2i_pipe_close.argtypes = [vp]
+    L.b2i_pipe_close.restype = None
     _lib = L
     return L
 
@@ -255,3 +277,41 @@ def partition_lpt(descs, parts: int):
     if rc != OK:
         raise B2IError(f"b2i_partition_lpt: {rc}")
     return [int(owner[i]) for i in range(n)], [int(x) for x in load]
+
+
+class Pipe:
+    """b2i_pipe over an in-memory archive (bytes / ctypes buffer / address) or a fill callback."""
+
+    def __init__(self, ctxs, descs, mem=None, mem_size=0, fill=None, window_out=0, first_window_out=0,
+                 depth=0, copy_threads=0):
+        self.L = lib()
+        self.n = len(descs)
+        self._keep = (mem, descs)
+        arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        opts = PipeOpts(window_out, first_window_out, depth, copy_threads)
+        self._cb = FILL_FN(fill) if fill is not None else C.cast(None, FILL_FN)
+        h = C.c_void_p()
+        rc = self.L.b2i_pipe_open(arr, len(ctxs), _addr(mem) if mem is not None else None, mem_size, self._cb,
+                                  None, descs, self.n, C.byref(opts), C.byref(h))
+        if rc != OK:
+            raise B2IError(f"b2i_pipe_open: {rc}")
+        self.h = h
+
+    def get(self, idx):
+        out, inp, res = C.c_void_p(), C.c_void_p(), StreamResult()
+        rc = self.L.b2i_pipe_get(self.h, idx, C.byref(out), C.byref(inp), C.byref(res))
+        if rc != OK:
+            raise B2IError(f"b2i_pipe_get({idx}): {rc} {self.L.b2i_pipe_error(self.h).decode()}")
+        return out.value, inp.value, res
+
+    def release(self, idx):
+        self.L.b2i_pipe_release(self.h, idx)
+
+    @property
+    def windows(self):
+        return int(self.L.b2i_pipe_window_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.b2i_pipe_close(self.h)
+            self.h = None

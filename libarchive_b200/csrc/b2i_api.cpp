@@ -63,7 +63,8 @@ struct b2i_ctx {
 	/* pipelined host path: copy-in / compute / copy-out streams, and a reusable
 	 * (grow-only) arena for the slice plans so that no call allocates */
 	cudaStream_t s_in, s_out, s_cmp[B2I_PIPE_STREAMS];
-	cudaStream_t s_team;     /* large streams (one CTA each) run beside the single-warp kernel */
+	cudaStream_t s_team[B2I_PIPE_STREAMS];   /* large streams (one CTA each) run beside the single-warp kernel,
+	                                           one team stream per compute stream so that slices overlap */
 	cudaEvent_t ev_free;
 	bool pipe_ready;
 	b2i_job jobs[B2I_MAX_JOBS];     /* host-buffer decodes in flight (b2i_submit / b2i_wait) */
@@ -91,6 +92,7 @@ struct b2i_plan {
 	uint8_t *h_block;
 	size_t block_bytes, results_off;
 	cudaStream_t stream;     /* where this plan's upload, kernels and result copy run */
+	cudaStream_t team_stream;
 	bool owns_memory;        /* false: d_block / h_block live in the context's arena */
 	uint8_t *out_mirror;     /* host-mapped twin of the output (inflated bytes are stored to both) */
 	size_t batch_streams;    /* deflate streams of the whole batch this plan is a slice of (0: just this plan) */
@@ -198,7 +200,8 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 			cudaEventDestroy(J->ev_done);
 		}
 	}
-	if (c->s_team) cudaStreamDestroy(c->s_team);
+	for (int i = 0; i < B2I_PIPE_STREAMS; i++)
+		if (c->s_team[i]) cudaStreamDestroy(c->s_team[i]);
 	if (c->pipe_ready) {
 		cudaStreamDestroy(c->s_in);
 		cudaStreamDestroy(c->s_out);
@@ -278,7 +281,7 @@ static size_t plan_block_bound(size_t n, size_t stored_bytes)
 
 /* mem_d / mem_h: caller-provided (arena) memory of mem_cap bytes, or NULL to allocate */
 static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cudaStream_t stream,
-    cudaStream_t upload_stream, uint8_t *mem_d, uint8_t *mem_h, size_t mem_cap, b2i_plan **out)
+    cudaStream_t upload_stream, uint8_t *mem_d, uint8_t *mem_h, size_t mem_cap, b2i_plan **out, int team_lane = 0)
 {
 	if (c == NULL || out == NULL || (n && descs == NULL) || n > 0x7fffffffu)
 		return fail(c, B2I_E_INVAL, "b2i_plan_create: bad arguments");
@@ -404,10 +407,13 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 	p->d_results = (B2iResult *)(p->d_block + o_results);
 
 	if (!big.empty()) {
-		if (c->s_team == NULL && cudaStreamCreateWithFlags(&c->s_team, cudaStreamNonBlocking) != cudaSuccess) {
+		team_lane %= B2I_PIPE_STREAMS;
+		if (c->s_team[team_lane] == NULL &&
+		    cudaStreamCreateWithFlags(&c->s_team[team_lane], cudaStreamNonBlocking) != cudaSuccess) {
 			b2i_plan_destroy(p);
 			return fail(c, B2I_E_CUDA, "team stream");
 		}
+		p->team_stream = c->s_team[team_lane];
 		if (cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
 		    cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
 			b2i_plan_destroy(p);
@@ -460,7 +466,7 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 		 * streams occupy the SMs while they last and the team CTAs fill in behind them */
 		CU(c, cudaMemsetAsync(p->d_counter, 0, 8, p->stream));
 		CU(c, cudaEventRecord(p->ev_fork, p->stream));
-		CU(c, cudaStreamWaitEvent(c->s_team, p->ev_fork, 0));
+		CU(c, cudaStreamWaitEvent(p->team_stream, p->ev_fork, 0));
 	}
 	if (p->n_deflate) {
 		if (!p->n_big)
@@ -480,8 +486,8 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 	if (p->n_big) {
 		CU(c, b2i_launch_inflate_team((const uint8_t *)d_in, in_bytes, (uint8_t *)d_out, p->out_mirror, p->d_descs,
 		    p->d_results, p->d_order + p->n_deflate, p->n_big, p->d_counter + 1, c->d_crc_tab, c->d_xp8,
-		    c->d_scratch, c->d_slot_busy, c->num_sms, c->s_team));
-		CU(c, cudaEventRecord(p->ev_join, c->s_team));
+		    c->d_scratch, c->d_slot_busy, c->num_sms, p->team_stream));
+		CU(c, cudaEventRecord(p->ev_join, p->team_stream));
 		c->launches++;
 	}
 	if (p->n_stored) {
@@ -739,21 +745,37 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		 * of one direction execute in submission order, so the small plan upload
 		 * must not queue behind later slices' data.) */
 		rc = b2i_plan_build(c, sd, sn, cs, c->s_in, J->arena_d + arena_off[s], J->arena_h + arena_off[s],
-		    align_up(plan_block_bound(sn, stored_bytes), 256), &plans[s]);
+		    align_up(plan_block_bound(sn, stored_bytes), 256), &plans[s], (int)(s % B2I_PIPE_STREAMS));
 		if (rc != B2I_OK)
 			break;
-		uint64_t lo = ~0ull, hi = 0;
-		for (size_t i = 0; i < sn; i++) {
-			if (sd[i].method != B2I_METHOD_DEFLATE && sd[i].method != B2I_METHOD_STORED)
-				continue;
-			lo = std::min<uint64_t>(lo, sd[i].in_off);
-			hi = std::max<uint64_t>(hi, sd[i].in_off + sd[i].in_len);
-		}
-		if (lo < hi) {
-			lo &= ~(uint64_t)15;
-			cudaError_t e = cudaMemcpyAsync(J->d_in + lo, (const uint8_t *)host_in + lo, hi - lo,
-			    cudaMemcpyHostToDevice, c->s_in);
-			if (e != cudaSuccess) { rc = fail(c, B2I_E_CUDA, "H2D: %s", cudaGetErrorString(e)); break; }
+		/* the slice's input: runs of streams that follow each other in the source (one run
+		 * for a contiguous range of an archive; several when the caller handed us a
+		 * subset, e.g. one GPU's share of an LPT partition) */
+		{
+			uint64_t lo = ~0ull, hi = 0;
+			bool bad = false;
+			auto flush_in = [&]() {
+				if (lo < hi) {
+					lo &= ~(uint64_t)15;
+					cudaError_t e = cudaMemcpyAsync(J->d_in + lo, (const uint8_t *)host_in + lo, hi - lo,
+					    cudaMemcpyHostToDevice, c->s_in);
+					if (e != cudaSuccess) { rc = fail(c, B2I_E_CUDA, "H2D: %s", cudaGetErrorString(e)); bad = true; }
+				}
+				lo = ~0ull; hi = 0;
+			};
+			for (size_t i = 0; i < sn && !bad; i++) {
+				if (sd[i].method != B2I_METHOD_DEFLATE && sd[i].method != B2I_METHOD_STORED)
+					continue;
+				const uint64_t a = sd[i].in_off, b = sd[i].in_off + sd[i].in_len;
+				if (lo < hi && (a + (256u << 10) < lo || a > hi + (256u << 10)))
+					flush_in();
+				lo = std::min<uint64_t>(lo, a);
+				hi = std::max<uint64_t>(hi, b);
+			}
+			if (!bad)
+				flush_in();
+			if (bad)
+				break;
 		}
 		if (cudaEventRecord(J->ev_in[s], c->s_in) != cudaSuccess ||
 		    cudaStreamWaitEvent(cs, J->ev_in[s], 0) != cudaSuccess) {
@@ -770,19 +792,32 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		}
 		/* copy-out stream, in order: the slice's decoded bytes, then its results */
 		if (host_out != NULL && mirror == NULL && plans[s]->max_out_end) {
+			/* runs of streams whose outputs follow each other (gaps are alignment padding
+			 * only): bytes between two runs belong to somebody else and are not touched */
 			uint64_t olo = ~0ull, ohi = 0;
-			for (size_t i = 0; i < sn; i++) {
-				if (sd[i].method == B2I_METHOD_DEFLATE ||
-				    (sd[i].method == B2I_METHOD_STORED && !(sd[i].flags & B2I_F_NO_COPY))) {
-					olo = std::min<uint64_t>(olo, sd[i].out_off);
-					ohi = std::max<uint64_t>(ohi, sd[i].out_off + sd[i].out_cap);
+			bool bad = false;
+			auto flush_out = [&]() {
+				if (olo < ohi && ohi <= out_bytes) {
+					cudaError_t e = cudaMemcpyAsync((uint8_t *)host_out + olo, J->d_out + olo, ohi - olo,
+					    cudaMemcpyDeviceToHost, c->s_out);
+					if (e != cudaSuccess) { rc = fail(c, B2I_E_CUDA, "D2H: %s", cudaGetErrorString(e)); bad = true; }
 				}
+				olo = ~0ull; ohi = 0;
+			};
+			for (size_t i = 0; i < sn && !bad; i++) {
+				if (!(sd[i].method == B2I_METHOD_DEFLATE ||
+				    (sd[i].method == B2I_METHOD_STORED && !(sd[i].flags & B2I_F_NO_COPY))))
+					continue;
+				const uint64_t a = sd[i].out_off, b = sd[i].out_off + sd[i].out_cap;
+				if (olo < ohi && (a < ohi || a > ohi + 15))
+					flush_out();
+				olo = std::min<uint64_t>(olo, a);
+				ohi = std::max<uint64_t>(ohi, b);
 			}
-			if (olo < ohi && ohi <= out_bytes) {
-				cudaError_t e = cudaMemcpyAsync((uint8_t *)host_out + olo, J->d_out + olo, ohi - olo,
-				    cudaMemcpyDeviceToHost, c->s_out);
-				if (e != cudaSuccess) { rc = fail(c, B2I_E_CUDA, "D2H: %s", cudaGetErrorString(e)); break; }
-			}
+			if (!bad)
+				flush_out();
+			if (bad)
+				break;
 		}
 		if (cudaMemcpyAsync(plans[s]->h_block + plans[s]->results_off, plans[s]->d_results,
 		    sn * sizeof(B2iResult), cudaMemcpyDeviceToHost, c->s_out) != cudaSuccess) {

@@ -77,7 +77,7 @@ struct B2iResult {
 /* -DB2I_PHASE_CLOCKS (make prof): per-phase cycle counters, summed over all warps,
  * printed and cleared by b2i_ctx_sync.  Profiling builds only. */
 #if defined(B2I_PHASE_CLOCKS) && !defined(B2I_HOST_EMUL)
-static __device__ unsigned long long g_b2i_phase[8];
+static __device__ unsigned long long g_b2i_phase[16];
 #define PH_DECL()      long long ph_t_ = clock64()
 #define PH_ADD(slot)   do { long long n_ = clock64(); if (b2i_lane() == 0) atomicAdd(&g_b2i_phase[slot], (unsigned long long)(n_ - ph_t_)); ph_t_ = n_; } while (0)
 #define PH_COUNT(slot, v) do { if (b2i_lane() == 0) atomicAdd(&g_b2i_phase[slot], (unsigned long long)(v)); } while (0)
@@ -93,3 +93,10 @@ static __device__ unsigned long long g_b2i_phase[8];
 #define PH_CRC    4
 #define PH_BATCH  5   /* count of resolve batches in LP */
 #define PH_STORED 6
+#define PH_TPASS  8   /* team: decode passes */
+#define PH_TEXP   9   /* team: expand */
+#define PH_TSWEEP 10  /* team: pointer sweep */
+#define PH_TFLUSH 11  /* team: flush */
+#define PH_TPLAN  12  /* team: hist reload + chunk planning */
+#define PH_TROUNDS 13
+#define PH_TPASSES 14

@@ -36,7 +36,10 @@ __global__ void b2i_phase_dump_kernel()
 	printf("B2I_PHASE header=%llu lpdec=%llu lpres=%llu unif=%llu crc=%llu batches=%llu stored=%llu\n",
 	    g_b2i_phase[0], g_b2i_phase[1], g_b2i_phase[2], g_b2i_phase[3], g_b2i_phase[4], g_b2i_phase[5],
 	    g_b2i_phase[6]);
-	for (int i = 0; i < 8; i++) g_b2i_phase[i] = 0;
+	printf("B2I_TEAM passes=%llu expand=%llu sweep=%llu flush=%llu plan=%llu rounds=%llu emit_passes=%llu expand_warp_iters=%llu\n",
+	    g_b2i_phase[8], g_b2i_phase[9], g_b2i_phase[10], g_b2i_phase[11], g_b2i_phase[12], g_b2i_phase[13],
+	    g_b2i_phase[14], g_b2i_phase[15]);
+	for (int i = 0; i < 16; i++) g_b2i_phase[i] = 0;
 }
 void b2i_phase_dump(cudaStream_t st) { b2i_phase_dump_kernel<<<1, 1, 0, st>>>(); }
 #endif
@@ -118,6 +121,8 @@ b2i_inflate_team_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8
 		while (atomicCAS(&slot_busy[slot], 0u, 1u) != 0u)
 			slot = slot + 1 == nslots ? 0 : slot + 1;
 		ts->scratch[w] = scratch + (size_t)slot * LP_SCRATCH_WORDS;
+		if (w == 0)
+			team_init(ts);
 	}
 	slot = __shfl_sync(B2I_FULL, slot, 0);
 	__syncthreads();
@@ -139,7 +144,7 @@ b2i_inflate_team_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8
 		}
 		team_command(ts, TC_QUIT);
 	} else {
-		team_serve(ts, w);
+		team_serve(ts, w, sm);
 	}
 	if (lane == 0) {
 		__threadfence();

@@ -64,7 +64,11 @@ struct LpOut {
  * code or the end of the stream (`hard_end`).  Lanes with run == false keep
  * out of it.  EMIT: write tokens to tok[0..nsym).
  */
-template <bool EMIT>
+/* TSTRIDE: distance between consecutive tokens of one lane.  1: every lane owns a
+ * contiguous run (the single-warp resolution reads one lane's tokens with all 32 lanes);
+ * 32: token k of lane l sits at [32 k + l], so that 32 lanes writing - or, in the team
+ * kernel's expand step, reading - "their next token" touch one or two 128-byte lines. */
+template <bool EMIT, int TSTRIDE = 1>
 B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uint32_t max_word,
     bool run, uint32_t start, uint32_t nominal_end, uint32_t hard_end, uint32_t *tok, LpOut &o)
 {
@@ -95,15 +99,7 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 		LP_LOAD();
 		LP_DROP(start & 31u);
 	}
-#ifdef B2I_EMUL_TRACE
-	unsigned long iters_ = 0;
-#endif
 	while (__any_sync(B2I_FULL, active)) {
-#ifdef B2I_EMUL_TRACE
-		if (++iters_ == 3000 && active)
-			fprintf(stderr, "lp_pass stuck: lane %u start %u widx %u cnt %d ns %u stop_at %u hard_end %u wbase %u max_word %u\n",
-			    b2i_lane(), start, widx, cnt, ns, stop_at, hard_end, wbase, max_word);
-#endif
 		if (!active)
 			continue;
 		if (cnt <= 30)
@@ -149,7 +145,7 @@ B2I_DEV void lp_pass(const WarpSmem *sm, const uint32_t *gw, uint32_t wbase, uin
 		}
 		B2I_CHECK(ns < LP_CAP);
 		if (EMIT) {
-			tok[ns] = token;
+			tok[ns * TSTRIDE] = token;
 			lastb = token >> 16;
 			nb += lastb;
 		}

@@ -85,6 +85,10 @@ struct __align__(16) TeamShared {
 	uint32_t ck_err;                    /* earliest failure: (chunk byte offset << 1) | overflow */
 	uint32_t hist_pos;                  /* TEAM_NOERR: the ring does not mirror the output */
 	uint32_t next_seg;                  /* segment size the last round suggests for the next */
+	uint32_t stage_words;               /* words of the round's input staged in sym[] (0: read global memory) */
+	uint32_t stage_lead;                /* staged word 0 sits this many words into the 16-byte aligned copy */
+	uint32_t stage_parity;
+	unsigned long long stage_bar;       /* mbarrier of the bulk copy */
 	const uint8_t *cp_src;
 	uint8_t *cp_dst;
 	uint32_t cp_n;
@@ -112,22 +116,87 @@ static inline uint32_t pack_even_bytes(uint32_t a, uint32_t b)
 }
 #endif
 
+/*
+ * The compressed bytes of a round are staged into shared memory (the chunk buffer is
+ * idle while the lanes decode) by ONE 1-D TMA bulk copy (cp.async.bulk + mbarrier
+ * complete_tx), so that the 256 lanes stream their segments from shared memory instead
+ * of chasing 4-byte words through L1/L2.  Word i of the stage is input word
+ * min(wbase + i, max_word), exactly what lp_pass would have read from global memory.
+ */
+B2I_DEV void team_stage_input(TeamShared *ts, unsigned w)
+{
+	const unsigned tid = 32 * w + b2i_lane();
+	const uint32_t nwords = ts->stage_words;
+	if (nwords == 0)
+		return;
+	const uint32_t wbase = ts->wbase, max_word = ts->max_word;
+	const uint32_t lead = wbase & 3u;                  /* words in front of wbase in its 16-byte unit */
+	const uint32_t first = wbase - lead;               /* multiple of 4 words: 16-byte aligned */
+	uint32_t avail = max_word + 1u - first;            /* words that exist from there (multiple of 4) */
+	uint32_t want = (nwords + lead + 3u) & ~3u;
+	const uint32_t copy = want < avail ? want : avail;
+	uint32_t *dst = (uint32_t *)ts->sym;
+#ifndef B2I_HOST_EMUL
+	if (tid == 0) {
+		const uint32_t bar = smem_addr(&ts->stage_bar);
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(copy * 4u) : "memory");
+		asm volatile(
+		    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		    :: "r"(smem_addr(dst)), "l"(ts->gw + first), "r"(copy * 4u), "r"(bar) : "memory");
+	}
+	{
+		const uint32_t bar = smem_addr(&ts->stage_bar);
+		const uint32_t parity = ts->stage_parity;
+		uint32_t done;
+		do {
+			asm volatile(
+			    "{\n\t.reg .pred p;\n\t"
+			    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			    "selp.u32 %0, 1, 0, p;\n\t}"
+			    : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+		} while (!done);
+	}
+#else
+	for (uint32_t i = tid; i < copy; i += TEAM_LANES)
+		dst[i] = ts->gw[first + i];
+	team_sync();
+#endif
+	/* past the end of the input: the last word repeats (lp_pass clamps its index) */
+	if (copy < want) {
+		team_sync();
+		const uint32_t last = dst[copy - 1];
+		for (uint32_t i = copy + tid; i < want; i += TEAM_LANES)
+			dst[i] = last;
+	}
+	team_sync();
+	if (tid == 0)
+		ts->stage_parity ^= 1u;
+}
+
 template <bool EMIT>
-B2I_DEV void team_do_pass(TeamShared *ts, unsigned w)
+B2I_DEV void team_do_pass(TeamShared *ts, unsigned w, const WarpSmem *tables)
 {
 	const unsigned lane = b2i_lane();
 	const unsigned gid = 32 * w + lane;
 	const bool run = ts->run[gid] != 0;
 	LpOut o;
 	o.exit = 0; o.nsym = 0; o.term = LT_NONE; o.nbytes = 0;
-#ifdef B2I_EMUL_TRACE
-	if (lane == 0) fprintf(stderr, "  pass warp %u enter\n", w);
-#endif
-	lp_pass<EMIT>(ts->tables, ts->gw, ts->wbase, ts->max_word, run, ts->start[gid],
-	    ts->p0 + (gid + 1u) * ts->seg, ts->hard_end, ts->scratch[w] + lane * LP_CAP, o);
-#ifdef B2I_EMUL_TRACE
-	if (lane == 0) fprintf(stderr, "  pass warp %u exit\n", w);
-#endif
+	const uint32_t nominal_end = ts->p0 + (gid + 1u) * ts->seg;
+	uint32_t start = ts->start[gid];
+	if (!EMIT && gid != 0) {
+		/* pass A only looks for the place where this lane's decoder crosses into the next
+		 * segment: starting one margin EARLIER gives it that much more input to fall into
+		 * step with the true symbol sequence before it gets there */
+		const uint32_t margin = ts->seg;
+		start = start - ts->p0 > margin ? start - margin : ts->p0;
+	}
+	if (ts->stage_words)
+		lp_pass<EMIT, 32>(tables, (const uint32_t *)ts->sym + ts->stage_lead, 0u, ts->stage_words - 1u, run, start,
+		    nominal_end, ts->hard_end, ts->scratch[w] + lane, o);
+	else
+		lp_pass<EMIT, 32>(tables, ts->gw, ts->wbase, ts->max_word, run, start,
+		    nominal_end, ts->hard_end, ts->scratch[w] + lane, o);
 	if (run) {
 		ts->exit_[gid] = o.exit;
 		ts->term[gid] = o.term;
@@ -146,6 +215,12 @@ B2I_DEV void team_chunk(TeamShared *ts, unsigned w)
 	const uint32_t g0 = ts->ck_g0, g1 = ts->ck_g1;
 	const bool partial = ts->ck_partial != 0;
 	uint8_t *out = ts->out, *mir = ts->mir;
+#if defined(B2I_PHASE_CLOCKS) && !defined(B2I_HOST_EMUL)
+	long long tph_ = clock64();
+#define TPH(slot) do { long long n_ = clock64(); if (tid == 0) atomicAdd(&g_b2i_phase[slot], (unsigned long long)(n_ - tph_)); tph_ = n_; } while (0)
+#else
+#define TPH(slot) do { } while (0)
+#endif
 
 	/* 0. the history ring must hold the 32 KiB in front of the chunk (it does unless
 	 * a stored block or the uniform tail wrote output since the last chunk) */
@@ -155,67 +230,98 @@ B2I_DEV void team_chunk(TeamShared *ts, unsigned w)
 			ts->hist[p & (TEAM_HIST - 1)] = load_fresh(out + p);
 	}
 	team_sync();
+	TPH(PH_TPLAN);
 
-	/* 1. expand: one region per lane, one symbol per step */
+	/* 1. expand: one region per lane, one symbol per lane and step; the warp stays
+	 * converged (a lane that fetches a token and a lane in the middle of a match run the
+	 * same few predicated instructions), so a step costs one pass over the loop body */
 	{
 		const uint32_t r = g0 + tid;
-		if (r < g1) {
-			const uint32_t *rt = ts->scratch[r >> 5] + (r & 31u) * LP_CAP;
-			const uint32_t ntok = ts->nsym[r];
-			uint32_t j = ts->tokpos[r];
-			const uint32_t rel0 = (ts->roff[r] + ts->rdone[r]) - (ts->roff[g0] + ts->rdone[g0]);
-			uint32_t pos = lead + rel0;
+		bool active = r < g1;
+		const uint32_t *rt = ts->scratch[0];
+		uint32_t ntok = 0, j = 0, pos = lead, lim = lead, rem = 0, d = 0;
+		/* the next four tokens are kept in registers (token k of a lane sits at [32 k]):
+		 * a freshly loaded one is not needed before three others have been consumed */
+		uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+		bool cap_bound = false;
+		if (active) {
+			rt = ts->scratch[r >> 5] + (r & 31u);
+			ntok = ts->nsym[r];
+			j = ts->tokpos[r];
+			pos = lead + (ts->roff[r] + ts->rdone[r]) - (ts->roff[g0] + ts->rdone[g0]);
 			/* bytes the chunk may hold: the buffer, or what is left of the output capacity */
 			const uint32_t room = ts->cap - abs0;
-			const bool cap_bound = room < TEAM_CHUNK - lead;
-			const uint32_t lim = lead + (cap_bound ? room : TEAM_CHUNK - lead);
-			uint32_t rem = 0, d = 0;
-			uint32_t nxt = j < ntok ? rt[j] : 0;
-			bool stop = false;
-			while (!stop) {
+			cap_bound = room < TEAM_CHUNK - lead;
+			lim = lead + (cap_bound ? room : TEAM_CHUNK - lead);
+			q0 = j < ntok ? rt[32u * j] : 0;
+			q1 = j + 1 < ntok ? rt[32u * (j + 1)] : 0;
+			q2 = j + 2 < ntok ? rt[32u * (j + 2)] : 0;
+			q3 = j + 3 < ntok ? rt[32u * (j + 3)] : 0;
+		}
+		while (__any_sync(B2I_FULL, active)) {
+			if (active) {
+				uint32_t v = 0;
+				bool emit = true;
 				if (rem == 0) {
-					if (j >= ntok)
-						break;
-					const uint32_t t = nxt;
+					const uint32_t t = q0;
 					const uint32_t len = t >> 16;
-					if (pos + len > lim) {
+					if (j >= ntok) {
+						active = false;
+						emit = false;
+					} else if (pos + len > lim) {
 						/* does not fit: the chunk is full (partial region) or the output is */
 						if (cap_bound || !partial)
 							team_atomic_min(&ts->ck_err, ((pos - lead) << 1) | 1u);
-						break;
-					}
-					j++;
-					nxt = rt[j < ntok ? j : j - 1];
-					if (len == 1) {
-						B2I_CHECK(pos < TEAM_CHUNK);
-						ts->sym[pos++] = (uint16_t)(t & 0xffu);
-						continue;
-					}
-					d = t & 0xffffu;
-					rem = len;
-					if (d > abs0 + (pos - lead)) {          /* zlib: invalid distance too far back */
-						team_atomic_min(&ts->ck_err, (pos - lead) << 1);
-						j--;
-						stop = true;
-						continue;
+						active = false;
+						emit = false;
+					} else {
+						j++;
+						q0 = q1; q1 = q2; q2 = q3;
+						q3 = rt[32u * (j + 3 < ntok ? j + 3 : j)];
+						if (len == 1) {
+							v = t & 0xffu;
+						} else {
+							d = t & 0xffffu;
+							rem = len;
+							if (d > abs0 + (pos - lead)) {      /* zlib: invalid distance too far back */
+								team_atomic_min(&ts->ck_err, (pos - lead) << 1);
+								j--;
+								active = false;
+								emit = false;
+							}
+						}
 					}
 				}
-				B2I_CHECK(pos < TEAM_CHUNK);
-				if (pos >= d + lead)
-					ts->sym[pos] = (uint16_t)(TS_PTR | (pos - d));
-				else
-					ts->sym[pos] = ts->hist[(abs0 + (pos - lead) - d) & (TEAM_HIST - 1)];
-				pos++;
-				rem--;
+				if (emit) {
+					if (rem != 0) {
+						/* up to four symbols of a match per step: independent stores */
+						const uint32_t nn = rem < 4u ? rem : 4u;
+#pragma unroll
+						for (uint32_t k = 0; k < 4u; k++) {
+							const uint32_t p = pos + k;
+							if (k < nn) {
+								B2I_CHECK(p < TEAM_CHUNK);
+								ts->sym[p] = (uint16_t)(p >= d + lead ? (TS_PTR | (p - d))
+								    : (uint32_t)ts->hist[(abs0 + (p - lead) - d) & (TEAM_HIST - 1)]);
+							}
+						}
+						pos += nn;
+						rem -= nn;
+					} else {
+						B2I_CHECK(pos < TEAM_CHUNK);
+						ts->sym[pos++] = (uint16_t)v;
+					}
+				}
 			}
-			if (partial) {
-				ts->tokpos[r] = j;
-				ts->rdone[r] += pos - lead;
-				ts->ck_len = pos - lead;
-			}
+		}
+		if (r < g1 && partial) {
+			ts->tokpos[r] = j;
+			ts->rdone[r] += pos - lead;
+			ts->ck_len = pos - lead;
 		}
 	}
 	team_sync();
+	TPH(PH_TEXP);
 
 	/* 2. sweep: pointers -> bytes, every warp its slice, in order */
 	uint32_t T = ts->ck_len;
@@ -246,6 +352,7 @@ B2I_DEV void team_chunk(TeamShared *ts, unsigned w)
 		}
 	}
 	team_sync();
+	TPH(PH_TSWEEP);
 
 	/* 3. flush: 16 symbols -> 16 bytes per lane and step, to global memory and the ring */
 	{
@@ -279,6 +386,8 @@ B2I_DEV void team_chunk(TeamShared *ts, unsigned w)
 		}
 	}
 	team_sync();
+	TPH(PH_TFLUSH);
+#undef TPH
 	if (tid == 0) {
 		ts->ck_len = T;
 		ts->hist_pos = abs0 + T;
@@ -343,46 +452,33 @@ B2I_DEV void team_crc(TeamShared *ts, unsigned w)
 }
 
 /* what the helper warps (1..TEAM_WARPS-1) do for the lifetime of the CTA */
-B2I_DEV void team_serve(TeamShared *ts, unsigned w)
+B2I_DEV void team_serve(TeamShared *ts, unsigned w, const WarpSmem *tables)
 {
 	for (;;) {
 		team_sync();
 		const uint32_t c = ts->cmd;
-#ifdef B2I_EMUL_TRACE
-		fprintf(stderr, "  serve %u.%u got cmd %u\n", w, b2i_lane(), c);
-#endif
 		if (c == TC_QUIT)
 			break;
-		if (c == TC_PASS_A)
-			team_do_pass<false>(ts, w);
-		else if (c == TC_PASS_EMIT)
-			team_do_pass<true>(ts, w);
+		if (c == TC_PASS_A) {
+			team_stage_input(ts, w);
+			team_do_pass<false>(ts, w, tables);
+		} else if (c == TC_PASS_EMIT)
+			team_do_pass<true>(ts, w, tables);
 		else if (c == TC_CHUNK)
 			team_chunk(ts, w);
 		else if (c == TC_COPY)
 			team_copy(ts, w);
 		else
 			team_crc(ts, w);
-#ifdef B2I_EMUL_TRACE
-		fprintf(stderr, "  serve %u.%u done cmd %u\n", w, b2i_lane(), c);
-#endif
 		team_sync();
 	}
 }
 
 B2I_DEV void team_command(TeamShared *ts, uint32_t c)
 {
-#ifdef B2I_EMUL_TRACE
-	if (b2i_lane() == 0)
-		fprintf(stderr, "cmd %u seg %u g0 %u g1 %u partial %u abs0 %u len %u m %u\n", c, ts->seg, ts->ck_g0, ts->ck_g1,
-		    ts->ck_partial, ts->ck_abs0, ts->ck_len, ts->m);
-#endif
 	if (b2i_lane() == 0)
 		ts->cmd = c;
 	fence_block();
-#ifdef B2I_EMUL_TRACE
-	fprintf(stderr, "  w0.%u at command sync %u\n", b2i_lane(), c);
-#endif
 	team_sync();
 }
 
@@ -421,12 +517,25 @@ B2I_DEV uint32_t team_crc_raw0(TeamShared *ts, const uint8_t *p, uint64_t n, con
 	return acc;
 }
 
+/* once per CTA (one thread), before the first barrier */
+B2I_DEV void team_init(TeamShared *ts)
+{
+	ts->stage_parity = 0;
+	ts->stage_words = 0;
+#ifndef B2I_HOST_EMUL
+	mbar_init(&ts->stage_bar);
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
 /* once per stream (warp 0) */
 B2I_DEV void team_stream_begin(TeamShared *ts, uint8_t *out, uint8_t *mir, uint32_t cap)
 {
 	if (b2i_lane() == 0) {
 		ts->hist_pos = TEAM_NOERR;
 		ts->next_seg = TEAM_SEG_INIT;
+		ts->stage_words = 0;
 		ts->out = out;
 		ts->mir = mir;
 		ts->cap = cap;
@@ -445,9 +554,6 @@ B2I_DEV int lp_block_team(TeamShared *ts, WarpSmem *sm, const uint8_t *gbase, ui
 	bool entered = false;
 
 	for (;;) {
-#ifdef B2I_EMUL_TRACE
-		fprintf(stderr, "  w0.%u round top P %llu end %llu\n", lane, (unsigned long long)P, (unsigned long long)end_bits);
-#endif
 		if (end_bits < P + TEAM_MIN_BITS) {
 			ret = 2;
 			break;
@@ -480,6 +586,13 @@ B2I_DEV int lp_block_team(TeamShared *ts, WarpSmem *sm, const uint8_t *gbase, ui
 			ts->gw = (const uint32_t *)gbase;
 			ts->max_word = (uint32_t)(glimit >> 2) - 1u;
 			ts->tables = sm;
+			{
+				/* everything the lanes may read: the segments, one symbol past the last one
+				 * and the word the bit reader keeps in flight */
+				const uint32_t need = (p0 + TEAM_LANES * seg) / 32u + 6u;
+				ts->stage_words = need + 4u <= (TEAM_CHUNK * 2u) / 4u ? need : 0u;
+				ts->stage_lead = wbase & 3u;
+			}
 			ts->out = out;
 			ts->mir = mir;
 			ts->cap = cap;
@@ -496,9 +609,12 @@ B2I_DEV int lp_block_team(TeamShared *ts, WarpSmem *sm, const uint8_t *gbase, ui
 			ts->rdone[gid] = 0;
 		}
 		__syncwarp();
+		PH_DECL();
+		PH_COUNT(PH_TROUNDS, 1);
 		/* pass A, then emit passes until every lane starts at its predecessor's exit */
 		team_command(ts, TC_PASS_A);
-		team_do_pass<false>(ts, 0);
+		team_stage_input(ts, 0);
+		team_do_pass<false>(ts, 0, sm);
 		team_sync();
 		bool first = true;
 #ifdef B2I_HOST_EMUL
@@ -525,10 +641,12 @@ B2I_DEV int lp_block_team(TeamShared *ts, WarpSmem *sm, const uint8_t *gbase, ui
 #ifdef B2I_HOST_EMUL
 			if (lane == 0) g_lp_passes++;
 #endif
+			PH_COUNT(PH_TPASSES, 1);
 			team_command(ts, TC_PASS_EMIT);
-			team_do_pass<true>(ts, 0);
+			team_do_pass<true>(ts, 0, sm);
 			team_sync();
 		}
+		PH_ADD(PH_TPASS);
 		/* the first lane that met EOB / an invalid code / the end of input ends the round */
 		unsigned m = TEAM_LANES - 1;
 		for (unsigned w = TEAM_WARPS; w-- > 0;) {
@@ -590,13 +708,7 @@ B2I_DEV int lp_block_team(TeamShared *ts, WarpSmem *sm, const uint8_t *gbase, ui
 			__syncwarp();
 			team_command(ts, TC_CHUNK);
 			team_chunk(ts, 0);
-#ifdef B2I_EMUL_TRACE
-			fprintf(stderr, "  w0.%u chunk done\n", lane);
-#endif
 			team_sync();
-#ifdef B2I_EMUL_TRACE
-			fprintf(stderr, "  w0.%u past sync err %x len %u g %u m %u\n", lane, ts->ck_err, ts->ck_len, g, m);
-#endif
 			PH_COUNT(PH_BATCH, 1);
 			const uint32_t err = ts->ck_err;
 			outp = abs0 + ts->ck_len;

@@ -233,6 +233,26 @@ def split_text(total: int, each: int, seed: int):
     return [blob[i:i + each] for i in range(0, total, each)]
 
 
+def text_corpus_parts(total: int, each: int, seed: int, base: int = 64 << 20):
+    """`total` bytes of synthetic text in pieces of `each` bytes for the LARGE configs: the
+    generator above runs at ~15 MB/s, so beyond `base` bytes the pieces are cut from
+    rotations of one `base`-byte text (rotation j starts 4099*j bytes in): same statistics,
+    every piece a different byte string."""
+    if total <= base:
+        return split_text(total, each, seed)
+    blob = synth_text(base, seed)
+    parts, rot = [], 0
+    while len(parts) * each < total:
+        r = (4099 * rot) % (base - each)
+        view = blob[r:] + blob[:r]
+        for i in range(0, base - each + 1, each):
+            parts.append(view[i:i + each])
+            if len(parts) * each >= total:
+                break
+        rot += 1
+    return parts
+
+
 def config1_zip_text64k(n_entries: int = 4096, entry: int = 65536, framing: str = "sizes",
                         seed: int = 12345) -> bytes:
     parts = split_text(n_entries * entry, entry, seed)

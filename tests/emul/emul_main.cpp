@@ -123,8 +123,11 @@ static void *team_lane_main(void *p)
 	tl_lane = a->lane;
 	tl_warp = &j->warp[a->w];
 	tl_team = &j->bar;
-	if (a->lane == 0)
+	if (a->lane == 0) {
 		j->ts.scratch[a->w] = j->scratch[a->w];
+		if (a->w == 0)
+			team_init(&j->ts);
+	}
 	team_sync();
 	if (a->w == 0) {
 		Ring ring;
@@ -133,7 +136,7 @@ static void *team_lane_main(void *p)
 		    j->d, &j->res, g_crc_tab, g_xp8);
 		team_command(&j->ts, TC_QUIT);
 	} else {
-		team_serve(&j->ts, a->w);
+		team_serve(&j->ts, a->w, &j->sm[0]);
 	}
 	return NULL;
 }
