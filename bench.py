@@ -201,7 +201,7 @@ def cpu_reference_run(archive, kind, steps, warmup, sample_units=None, procs=Non
             times, out_bytes, j = [], 0, {}
             t_start = time.perf_counter()
             for i in range(warmup + steps):
-                r = subprocess.run(cmd, capture_output=True, text=True, check=True, timeout=900)
+                r = subprocess.run(cmd, capture_output=True, text=True, check=True, timeout=300)
                 j = json.loads(r.stdout.strip().splitlines()[-1])
                 if j.get("bad"):
                     raise RuntimeError("reference reported errors: %s" % j)
@@ -459,7 +459,7 @@ def public_api_e2e(archive, kind, local_rank, K, W):
             cmd = [exe, path, "--mode", mode, "--steps", str(K), "--warmup", str(max(2, min(W, 3)))]
             if kind != "zip":
                 cmd.append("--raw")
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
             if r.returncode != 0:
                 out[mode] = {"error": (r.stderr or r.stdout).strip()[-300:]}
                 continue
@@ -480,9 +480,11 @@ def measure_config(rig, name, scale, rank, K, W, peak, with_cpu, seed_rank=None)
     h_in = L.b2i_host_alloc(in_bytes + 64)
     assert h_in
     C.memmove(h_in, archive, in_bytes)
+    note("  %s: generated in %.1fs, %d streams, device-resident" % (name, gen_s, len(descs)))
     step_ms, total_ms, launches, d_in, d_out = device_resident(rig, h_in, in_bytes, descs, max(out_bytes, 16), K, W)
     one_ms = two_ms = pipe_ms = None
     if out_bytes:
+        note("  %s: C-ABI e2e" % name)
         one_ms, two_ms, pipe_ms = abi_e2e(rig, h_in, in_bytes, descs, out_bytes, max(2, K // 2), W)
     L.b2i_device_free(ctx.h, d_in)
     L.b2i_device_free(ctx.h, d_out)
@@ -513,6 +515,7 @@ def measure_config(rig, name, scale, rank, K, W, peak, with_cpu, seed_rank=None)
                       "value": usz / (min(ms) * 1e-3) / 1e9}
     if with_cpu:
         try:
+            note("  %s: cpu baseline" % name)
             cb = cpu_reference_run(archive, kind, 1, 0, sample_units=cpu_sample_units(name, scale))
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the baseline must not sink the GPU number
@@ -573,7 +576,20 @@ def strong_scaling(rig, name, scale, rank, K, W):
 
 # --------------------------------------------------------------------------- main
 
+def note(msg):
+    """Progress on stderr (the driver keeps stdout for the one JSON line)."""
+    if os.environ.get("B2I_BENCH_QUIET") is None:
+        sys.stderr.write("[bench %7.1fs rank %s] %s\n" % (time.perf_counter() - T_START, os.environ.get("RANK", "0"), msg))
+        sys.stderr.flush()
+
+
+T_START = time.perf_counter()
+
+
 def main():
+    import faulthandler
+    # a hang must not eat the box: dump every thread's stack and leave
+    faulthandler.dump_traceback_later(int(os.environ.get("B2I_BENCH_WATCHDOG", "1500")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -627,8 +643,10 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     with_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+    note("headline %s" % head)
     hd, archive, kind = measure_config(rig, head, head_scale, rank, K, W, peak, with_cpu)
     clocks = sampler.stop()
+    note("headline done: %.1f GB/s device-resident" % hd["value"])
 
     # host link, this rank alone is meaningless at N > 1: all ranks copy at once
     nlink = 256 << 20
@@ -642,7 +660,9 @@ def main():
 
     # ---- e2e through libarchive's public API (drop-in library, separate process) --------
     rig.barrier()
+    note("public API e2e")
     api = public_api_e2e(archive, kind, local_rank, max(3, K // 4), W) if head != "stored1m" else None
+    note("public API e2e done: %s" % (api,))
     usz_all, = rig.reduce([float(hd["out_bytes_per_gpu"])], "sum")
     e2e = dict(hd.get("e2e", {}))
     e2e["c_abi_best"] = e2e.pop("value", None)
@@ -713,6 +733,7 @@ def main():
             if name == head:
                 continue
             try:
+                note("config %s" % name)
                 c, a_, _ = measure_config(rig, name, scale_of(name), rank, Kc, Wc, peak, with_cpu)
                 del a_
                 c["steps"], c["warmup"] = Kc, Wc
@@ -723,6 +744,7 @@ def main():
         if world > 1:
             strong = {}
             for name in ("bgzf64k", "mixed", "tiny4k"):
+                note("strong %s" % name)
                 strong[name] = strong_scaling(rig, name, scale_of(name), rank, Kc, Wc)
             line["strong"] = strong
 

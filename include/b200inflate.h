@@ -120,6 +120,7 @@ const char *b2i_last_error(const b2i_ctx *);      /* "" when none            */
 int  b2i_abi_version(void);
 int  b2i_device_count(void);
 int  b2i_ctx_sync(b2i_ctx *);
+int  b2i_ctx_device(const b2i_ctx *);            /* the device it was created on */
 /* how many kernels this context has launched so far (bench's gpu_launches) */
 uint64_t b2i_ctx_launch_count(const b2i_ctx *);
 
@@ -203,8 +204,8 @@ int  b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, uint64_t mem
                    const b2i_pipe_opts *opts, b2i_pipe **out);
 /* Blocks until stream idx is decoded.  *out_data: its bytes (NULL for B2I_F_NO_COPY
  * stored streams), *in_data: its compressed bytes as staged; both stay valid until
- * b2i_pipe_release moves past idx.  Asking for a stream in a later window drops the
- * windows in between that have not been started (read_data_skip). */
+ * b2i_pipe_release moves past idx or a stream of a LATER window is asked for (which
+ * gives up all earlier windows and drops those not yet started: read_data_skip). */
 int  b2i_pipe_get(b2i_pipe *, size_t idx, const void **out_data, const void **in_data,
                   b2i_stream_result *res);
 void b2i_pipe_release(b2i_pipe *, size_t idx);    /* streams < idx are done with */
@@ -262,6 +263,16 @@ typedef struct b2i_zip_index {
 } b2i_zip_index;
 
 int  b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char errbuf[128]);
+/* The same walk over a source that is not one memory image (a seekable file behind
+ * libarchive's read filters, archive_read_open_filename.c:389-461): `fetch` returns a
+ * pointer to [off, off + len) that stays valid until its next call, or NULL.  Reads the
+ * tail, the directory and the local headers (in ascending offset), nothing else. */
+typedef const uint8_t *(*b2i_fetch_fn)(void *user, uint64_t off, size_t len);
+int  b2i_zip_index_build_cb(b2i_fetch_fn fetch, void *user, uint64_t size, b2i_zip_index *out,
+                            char errbuf[128]);
+/* seekable bid (zip.c:3720-3773): is there an acceptable end record in the last
+ * tail_len (<= 16 KiB) bytes of a file of file_size bytes?  1 / 0 */
+int  b2i_zip_probe_tail(const void *tail, size_t tail_len, uint64_t file_size);
 void b2i_zip_index_free(b2i_zip_index *);
 
 /* gzip / BGZF: member chain.  With a BGZF 'BC' extra subfield the whole chain

@@ -60,6 +60,7 @@ class PipeOpts(C.Structure):
 
 
 FILL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p)
+FETCH_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_uint64, C.c_size_t)
 
 EXPORTS = [
     "b2i_ctx_create", "b2i_ctx_destroy", "b2i_last_error", "b2i_abi_version", "b2i_device_count",
@@ -69,7 +70,7 @@ EXPORTS = [
     "b2i_crc32_combine", "b2i_zip_index_build", "b2i_zip_index_free", "b2i_gzip_peek_header",
     "b2i_gzip_scan_bgzf", "b2i_free", "b2i_partition_contiguous", "b2i_partition_lpt",
     "b2i_decode_host_multi", "b2i_pipe_open", "b2i_pipe_get", "b2i_pipe_release", "b2i_pipe_window_count",
-    "b2i_pipe_error", "b2i_pipe_close",
+    "b2i_pipe_error", "b2i_pipe_close", "b2i_zip_index_build_cb", "b2i_zip_probe_tail", "b2i_ctx_device",
 ]
 
 _lib = None
@@ -92,6 +93,7 @@ def lib():
     L.b2i_last_error.argtypes = [vp]
     L.b2i_last_error.restype = C.c_char_p
     L.b2i_ctx_sync.argtypes = [vp]
+    L.b2i_ctx_device.argtypes = [vp]
     L.b2i_ctx_launch_count.argtypes = [vp]
     L.b2i_ctx_launch_count.restype = u64
     L.b2i_host_alloc.argtypes = [sz]
@@ -127,6 +129,8 @@ def lib():
     L.b2i_free.restype = None
     L.b2i_partition_contiguous.argtypes = [C.POINTER(StreamDesc), sz, C.c_int, C.POINTER(sz)]
     L.b2i_partition_lpt.argtypes = [C.POINTER(StreamDesc), sz, C.c_int, C.POINTER(u32), C.POINTER(u64)]
+    L.b2i_zip_index_build_cb.argtypes = [FETCH_FN, vp, u64, C.POINTER(ZipIndex), C.c_char_p]
+    L.b2i_zip_probe_tail.argtypes = [vp, sz, u64]
     L.b2i_decode_host_multi.argtypes = [C.POINTER(vp), C.c_int, vp, sz, C.POINTER(StreamDesc), sz, vp, sz,
                                         C.POINTER(StreamResult)]
     L.b2i_pipe_open.argtypes = [C.POINTER(vp), C.c_int, vp, u64, FILL_FN, vp, C.POINTER(StreamDesc), sz,
@@ -242,6 +246,40 @@ def zip_index(archive: bytes):
         d["name"] = names[e.name_offset:e.name_offset + e.name_len]
         out.append(d)
     res = (out, ix.correction, bool(ix.has_encrypted_entries))
+    L.b2i_zip_index_free(C.byref(ix))
+    return res
+
+
+def zip_index_via_fetch(archive: bytes, chunk: int = 1 << 16):
+    """b2i_zip_index_build_cb over a source that only hands out bounded windows (what the
+    libarchive plugin does for file-backed archives): -> (entries, correction, encrypted,
+    bytes fetched)."""
+    L = lib()
+    ix = ZipIndex()
+    err = C.create_string_buffer(128)
+    keep = {"buf": None, "bytes": 0, "lo": 0, "hi": 0}
+
+    def fetch(user, off, length):
+        # a sliding read-ahead window, like the plugin keeps over its seekable source
+        if not (keep["lo"] <= off and off + length <= keep["hi"]):
+            n = max(length, min(chunk, len(archive) - off))
+            keep["buf"] = C.create_string_buffer(archive[off:off + n], n)
+            keep["lo"], keep["hi"] = off, off + n
+            keep["bytes"] += n
+        return C.addressof(keep["buf"]) + (off - keep["lo"])
+
+    cb = FETCH_FN(fetch)
+    rc = L.b2i_zip_index_build_cb(cb, None, len(archive), C.byref(ix), err)
+    if rc != OK:
+        raise B2IError(f"zip index: {rc} {err.value.decode()}")
+    names = C.string_at(ix.names, ix.names_len) if ix.names_len else b""
+    out = []
+    for i in range(ix.n):
+        e = ix.entries[i]
+        d = {f: getattr(e, f) for f, _ in ZipEntry._fields_}
+        d["name"] = names[e.name_offset:e.name_offset + e.name_len]
+        out.append(d)
+    res = (out, ix.correction, bool(ix.has_encrypted_entries), keep["bytes"])
     L.b2i_zip_index_free(C.byref(ix))
     return res
 

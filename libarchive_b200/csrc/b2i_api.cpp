@@ -215,6 +215,7 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 
 extern "C" const char *b2i_last_error(const b2i_ctx *c) { return c ? c->err : "no context"; }
 extern "C" uint64_t b2i_ctx_launch_count(const b2i_ctx *c) { return c ? c->launches : 0; }
+extern "C" int b2i_ctx_device(const b2i_ctx *c) { return c ? c->device : -1; }
 
 #ifdef B2I_PHASE_CLOCKS
 void b2i_phase_dump(cudaStream_t st);

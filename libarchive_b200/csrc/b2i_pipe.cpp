@@ -480,6 +480,15 @@ extern "C" int b2i_pipe_get(b2i_pipe *p, size_t idx, const void **out_data, cons
 				t.state = EMPTY;
 		p->cv_work.notify_all();
 	}
+	/* asking for a stream gives up every window in front of its own: their slots go back
+	 * to the ring (the pointers of an earlier get stay valid only within one window) */
+	if (p->win[wi].first > p->released_upto) {
+		p->released_upto = p->win[wi].first;
+		for (Slot &t : p->slots)
+			if (t.state == READY && t.window != (size_t)-1 && t.window < wi)
+				t.state = EMPTY;
+		p->cv_work.notify_all();
+	}
 	Slot &s = p->slots[wi % p->slots.size()];
 	for (;;) {
 		if (p->error != B2I_OK)

@@ -20,23 +20,34 @@
 #include "b200inflate.h"
 #include "b200_ctx_pool.h"
 
-#define POOL_MAX 4
+#define POOL_MAX 24
 
 static pthread_mutex_t pool_lock = PTHREAD_MUTEX_INITIALIZER;
-static b2i_ctx *pool[POOL_MAX];
+static struct { b2i_ctx *c; int dev; } pool[POOL_MAX];
 static int pool_n;
+
+/* a context on GPU `device` (the streaming engine spreads a large archive over several) */
+int
+b200_ctx_acquire_dev(int device, b2i_ctx **out)
+{
+	int i;
+
+	pthread_mutex_lock(&pool_lock);
+	for (i = 0; i < pool_n; i++)
+		if (pool[i].dev == device) {
+			*out = pool[i].c;
+			pool[i] = pool[--pool_n];
+			pthread_mutex_unlock(&pool_lock);
+			return (B2I_OK);
+		}
+	pthread_mutex_unlock(&pool_lock);
+	return (b2i_ctx_create(device, NULL, out));
+}
 
 int
 b200_ctx_acquire(b2i_ctx **out)
 {
-	pthread_mutex_lock(&pool_lock);
-	if (pool_n > 0) {
-		*out = pool[--pool_n];
-		pthread_mutex_unlock(&pool_lock);
-		return (B2I_OK);
-	}
-	pthread_mutex_unlock(&pool_lock);
-	return (b2i_ctx_create(0, NULL, out));
+	return (b200_ctx_acquire_dev(0, out));
 }
 
 void
@@ -50,7 +61,9 @@ b200_ctx_release(b2i_ctx *c, int healthy)
 	}
 	pthread_mutex_lock(&pool_lock);
 	if (pool_n < POOL_MAX) {
-		pool[pool_n++] = c;
+		pool[pool_n].c = c;
+		pool[pool_n].dev = b2i_ctx_device(c);
+		pool_n++;
 		c = NULL;
 	}
 	pthread_mutex_unlock(&pool_lock);

@@ -204,19 +204,79 @@ cmp_rec(const void *a, const void *b)
 	return x->idx < y->idx ? -1 : (x->idx > y->idx);
 }
 
-int
-b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char errbuf[128])
+/* ---- source access --------------------------------------------------------------
+ * The walk below never assumes the archive is one memory image: it asks for byte
+ * ranges through a fetch function (valid until the next call).  A memory image answers
+ * with a pointer into itself; the libarchive plugin answers from a sliding read-ahead
+ * window of its seekable source (archive_read_open_filename), so that indexing a large
+ * file reads the tail, the directory and the local headers - never the whole file into
+ * one buffer. */
+struct src {
+	b2i_fetch_fn fetch;
+	void *user;
+	uint64_t size;
+};
+
+static const uint8_t *
+mem_fetch(void *user, uint64_t off, size_t len)
 {
-	const uint8_t *base = archive;
+	(void)len;
+	return (const uint8_t *)user + off;
+}
+
+static const uint8_t *
+get(const struct src *s, uint64_t off, size_t len)
+{
+	if (off > s->size || s->size - off < len)
+		return NULL;
+	return s->fetch(s->user, off, len);
+}
+
+/* Does the last 16 KiB of a file hold an end-of-central-directory record the reader
+ * would accept (zip.c:3720-3773, 3635-3718)?  `tail` = the last tail_len bytes. */
+int
+b2i_zip_probe_tail(const void *tailp, size_t tail_len, uint64_t file_size)
+{
+	const uint8_t *tail = tailp;
+	long i;
+
+	if (tail == NULL || tail_len < 22 || tail_len > file_size)
+		return 0;
+	for (i = (long)tail_len - 22; i > 0; i--) {
+		const uint8_t *p = tail + i;
+		if (memcmp(p, "PK\005\006", 4) != 0)
+			continue;
+		{
+			uint64_t pos = file_size - tail_len + (uint64_t)i;
+			uint32_t cd_size = le32(p + 12), cd_off = le32(p + 16);
+			if (le16(p + 4) == 0 && le16(p + 6) == 0 && le16(p + 10) == le16(p + 8) &&
+			    (uint64_t)cd_off + cd_size <= pos)
+				return 1;
+			if (i >= 20 && memcmp(p - 20, "PK\006\007", 4) == 0 &&
+			    le32(p - 20 + 4) == 0 && le32(p - 20 + 16) == 1)
+				return 1;       /* the ZIP64 record itself is validated by the index walk */
+		}
+		break;
+	}
+	return 0;
+}
+
+int
+b2i_zip_index_build_cb(b2i_fetch_fn fetch, void *user, uint64_t size, b2i_zip_index *out, char errbuf[128])
+{
+	struct src S = { fetch, user, size };
 	int64_t cd_offset = -1, cd_adjusted = -1;
-	size_t tail, tail_start;
+	size_t tail;
+	uint64_t tail_start;
 	long i;
 	int found = 0;
 	struct dos_memo memo;
+	uint8_t *tailbuf = NULL, *cd = NULL;
+	const uint8_t *p;
 
 	memset(&memo, 0, sizeof(memo));
 
-	if (out == NULL || (archive == NULL && size))
+	if (out == NULL || fetch == NULL)
 		return B2I_E_INVAL;
 	memset(out, 0, sizeof(*out));
 	if (errbuf)
@@ -225,14 +285,17 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 		return err(errbuf, "empty file");
 
 	/* --- end of central directory: last PK\5\6 in the final 16 KiB, i > 0 --- */
-	tail = size < 16384 ? size : 16384;
+	tail = size < 16384 ? (size_t)size : 16384;
 	tail_start = size - tail;
+	if ((p = get(&S, tail_start, tail)) == NULL || (tailbuf = malloc(tail)) == NULL)
+		return p == NULL ? err(errbuf, "cannot read the end of the file") : B2I_E_NOMEM;
+	memcpy(tailbuf, p, tail);
 	for (i = (long)tail - 22; i > 0; i--) {
-		const uint8_t *p = base + tail_start + i;
+		p = tailbuf + i;
 		if (memcmp(p, "PK\005\006", 4) != 0)
 			continue;
 		{
-			int64_t pos = (int64_t)(tail_start + i);
+			int64_t pos = (int64_t)(tail_start + (uint64_t)i);
 			uint16_t disk = le16(p + 4);
 			uint32_t cd_size = le32(p + 12), cd_off = le32(p + 16);
 			if (disk == 0 && le16(p + 6) == 0 && le16(p + 10) == le16(p + 8) &&
@@ -245,8 +308,8 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 				const uint8_t *l = p - 20;
 				if (le32(l + 4) == 0 && le32(l + 16) == 1) {
 					uint64_t e64 = le64(l + 8);
-					if (e64 <= size && size - e64 >= 56) {
-						const uint8_t *q = base + e64;
+					const uint8_t *q;
+					if (e64 <= size && size - e64 >= 56 && (q = get(&S, e64, 56)) != NULL) {
 						uint64_t e64size = le64(q + 4) + 12;
 						if (e64size >= 56 && e64size <= 16384 && size - e64 >= e64size &&
 						    le32(q + 16) == 0 && le32(q + 20) == 0 &&
@@ -261,87 +324,113 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 		}
 		break;      /* only the last EOCD signature is examined */
 	}
+	free(tailbuf);
 	if (!found)
 		return err(errbuf, "no end-of-central-directory record");
 	if (cd_adjusted < 0 || (uint64_t)cd_adjusted > size)
 		return err(errbuf, "central directory offset out of range");
 
+	/* --- the directory region [cd_adjusted, size): kept in memory for the walk --- */
+	const size_t cdlen = (size_t)(size - (uint64_t)cd_adjusted);
+	if ((p = get(&S, (uint64_t)cd_adjusted, cdlen)) == NULL)
+		return err(errbuf, "cannot read the central directory");
+	if (fetch == mem_fetch) {
+		cd = NULL;                    /* a memory image: walk it in place */
+	} else {
+		if ((cd = malloc(cdlen ? cdlen : 1)) == NULL)
+			return B2I_E_NOMEM;
+		memcpy(cd, p, cdlen);
+		p = cd;
+	}
+	const uint8_t *base = p - cd_adjusted;   /* base + file offset, valid for offsets >= cd_adjusted only */
+
 	/* --- real start of the directory => correction for prepended data --- */
-	size_t pos = (size_t)cd_adjusted;
+	uint64_t pos = (uint64_t)cd_adjusted;
 	for (found = 0; pos + 4 < size; pos++) {
-		const uint8_t *p = base + pos;
-		if (p[0] == 'P' && p[1] == 'K' &&
-		    ((p[2] == 1 && p[3] == 2) || (p[2] == 5 && p[3] == 6) || (p[2] == 6 && p[3] == 6))) {
+		const uint8_t *c = base + pos;
+		if (c[0] == 'P' && c[1] == 'K' &&
+		    ((c[2] == 1 && c[3] == 2) || (c[2] == 5 && c[3] == 6) || (c[2] == 6 && c[3] == 6))) {
 			found = 1;
 			break;
 		}
 	}
-	if (!found || size - pos < 20)
+	if (!found || size - pos < 20) {
+		free(cd);
 		return err(errbuf, "central directory not found");
+	}
 	out->correction = (int64_t)pos - cd_offset;
 
 	/* --- pass 1: count records --- */
-	size_t n = 0, q = pos;
+	size_t n = 0;
+	uint64_t q = pos;
 	for (;;) {
+		const char *bad = NULL;
 		if (size - q < 4)
-			return err(errbuf, "truncated central directory");
-		if (memcmp(base + q, "PK\006\006", 4) == 0 || memcmp(base + q, "PK\005\006", 4) == 0)
+			bad = "truncated central directory";
+		else if (memcmp(base + q, "PK\006\006", 4) == 0 || memcmp(base + q, "PK\005\006", 4) == 0)
 			break;
-		if (memcmp(base + q, "PK\001\002", 4) != 0)
-			return err(errbuf, "Invalid central directory signature");
-		if (size - q < 46)
-			return err(errbuf, "truncated central directory");
-		size_t var = (size_t)le16(base + q + 28) + le16(base + q + 30);
-		if (size - q - 46 < var)
-			return err(errbuf, "Truncated ZIP file header");
-		q += 46 + var + le16(base + q + 32);
+		else if (memcmp(base + q, "PK\001\002", 4) != 0)
+			bad = "Invalid central directory signature";
+		else if (size - q < 46)
+			bad = "truncated central directory";
+		else if (size - q - 46 < (size_t)le16(base + q + 28) + le16(base + q + 30))
+			bad = "Truncated ZIP file header";
+		if (bad != NULL) {
+			free(cd);
+			return err(errbuf, bad);
+		}
+		q += 46 + (size_t)le16(base + q + 28) + le16(base + q + 30) + le16(base + q + 32);
 		if (q > size)
 			q = size;       /* a long comment may run off the end; the next read fails */
 		n++;
 	}
 
 	struct cdrec *recs = malloc((n ? n : 1) * sizeof(*recs));
-	if (recs == NULL)
+	if (recs == NULL) {
+		free(cd);
 		return B2I_E_NOMEM;
+	}
 
 	/* --- pass 2: decode records --- */
 	q = pos;
 	for (size_t k = 0; k < n; k++) {
-		const uint8_t *p = base + q;
+		const uint8_t *c = base + q;
 		struct cdrec *r = &recs[k];
-		uint32_t ext = le32(p + 38);
-		size_t nl = le16(p + 28), xl = le16(p + 30), cl = le16(p + 32);
+		uint32_t ext = le32(c + 38);
+		size_t nl = le16(c + 28), xl = le16(c + 30), cl = le16(c + 32);
 		const char *why = NULL;
-		uint64_t lho32 = le32(p + 42);
+		uint64_t lho32 = le32(c + 42);
 
 		memset(r, 0, sizeof(*r));
 		r->idx = (uint32_t)k;
-		r->system = p[5];
-		r->flags = le16(p + 8);
+		r->system = c[5];
+		r->flags = le16(c + 8);
 		if (r->flags & (ZIP_ENCRYPTED | ZIP_STRONG_ENCRYPTED))
 			out->has_encrypted_entries = 1;
-		r->method = (uint8_t)le16(p + 10);
-		r->mtime = dos_time(&memo, le32(p + 12));
-		r->crc = le32(p + 16);
-		r->csize = le32(p + 20);
-		r->usize = le32(p + 24);
+		r->method = (uint8_t)le16(c + 10);
+		r->mtime = dos_time(&memo, le32(c + 12));
+		r->crc = le32(c + 16);
+		r->csize = le32(c + 20);
+		r->usize = le32(c + 24);
 		/* the reference adds the correction BEFORE testing for 0xffffffff, so a
 		 * ZIP64 offset is only honoured when the correction is zero (zip.c:3985, :559) */
 		r->lho = lho32 + (uint64_t)out->correction;
-		if (p[5] == 3)
+		if (c[5] == 3)
 			r->mode = ext >> 16;
-		else if (p[5] == 0) {
+		else if (c[5] == 0) {
 			r->mode = (ext & 0x10) ? (IFDIR | 0775) : (IFREG | 0664);
 			if (ext & 0x01)
 				r->mode &= 0555 | IFMT;
 		} else
 			r->mode = 0;
-		if (apply_extra(p + 46 + nl, xl, r, 1, &why) != 0) {
+		if (apply_extra(c + 46 + nl, xl, r, 1, &why) != 0) {
 			free(recs);
+			free(cd);
 			return err(errbuf, why);
 		}
 		q += 46 + nl + xl + cl;
 	}
+	free(cd);
 
 	/* --- ascending local-header offset; first record of an offset wins --- */
 	qsort(recs, n, sizeof(*recs), cmp_rec);
@@ -351,17 +440,14 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 			recs[m++] = recs[k];
 
 	b2i_zip_entry *ents = calloc(m ? m : 1, sizeof(*ents));
-	size_t names_cap = 0;
-	for (size_t k = 0; k < m; k++)
-		if (recs[k].lho <= size && size - recs[k].lho >= 30)
-			names_cap += le16(base + recs[k].lho + 26);
-	char *names = malloc(names_cap ? names_cap : 1);
+	size_t names_cap = 64 * (m + 1);
+	char *names = malloc(names_cap);
 	if (ents == NULL || names == NULL) {
 		free(recs); free(ents); free(names);
 		return B2I_E_NOMEM;
 	}
 
-	/* --- pass 3: local headers --- */
+	/* --- pass 3: local headers, in ascending offset (sequential for the source) --- */
 	size_t names_len = 0;
 	for (size_t k = 0; k < m; k++) {
 		const struct cdrec *r = &recs[k];
@@ -379,17 +465,16 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 		e->ctime = r->ctime;
 		e->uid = r->uid;
 		e->gid = r->gid;
-		if (r->lho > size || size - r->lho < 30) {
+		if (r->lho > size || size - r->lho < 30 || (p = get(&S, r->lho, 30)) == NULL) {
 			e->warn |= B2I_ZW_TRUNCATED;
 			continue;
 		}
-		const uint8_t *p = base + r->lho;
 		if (memcmp(p, "PK\003\004", 4) != 0) {
 			e->warn |= B2I_ZW_BAD_LOCAL_HEADER;
 			continue;
 		}
 		size_t nl = le16(p + 26), xl = le16(p + 28);
-		if (size - r->lho - 30 < nl + xl) {
+		if (size - r->lho - 30 < nl + xl || (p = get(&S, r->lho, 30 + nl + xl)) == NULL) {
 			e->warn |= B2I_ZW_TRUNCATED;
 			continue;
 		}
@@ -407,6 +492,15 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 		e->system = p[5];
 		e->zip_flags = le16(p + 6);
 		e->method = (uint8_t)le16(p + 8);
+		if (names_len + nl > names_cap) {
+			char *nn;
+			names_cap = 2 * (names_len + nl);
+			if ((nn = realloc(names, names_cap)) == NULL) {
+				free(recs); free(ents); free(names);
+				return B2I_E_NOMEM;
+			}
+			names = nn;
+		}
 		e->name_offset = (uint32_t)names_len;
 		e->name_len = (uint16_t)nl;
 		memcpy(names + names_len, p + 30, nl);
@@ -464,6 +558,14 @@ b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char e
 	out->names = names;
 	out->names_len = names_len;
 	return B2I_OK;
+}
+
+int
+b2i_zip_index_build(const void *archive, size_t size, b2i_zip_index *out, char errbuf[128])
+{
+	if (archive == NULL && size)
+		return B2I_E_INVAL;
+	return b2i_zip_index_build_cb(mem_fetch, (void *)(uintptr_t)archive, size, out, errbuf);
 }
 
 void

@@ -84,6 +84,7 @@ json_str(FILE *f, const char *s)
  * (no seek, no skip), so that the ZIP STREAMING reader is the one that runs */
 static struct { const unsigned char *p; size_t left, blk; } g_src;
 static int g_stream_blk;
+static const char *g_file_path;     /* --file: archive_read_open_filename instead of open_memory */
 static int g_meta;      /* --meta: owner, access/change times, link target, encryption flags as well */
 
 static la_ssize_t
@@ -117,7 +118,8 @@ open_reader(const void *buf, size_t len, int raw, const char *opt)
 		g_src.left = len;
 		g_src.blk = (size_t)g_stream_blk;
 	}
-	if ((g_stream_blk > 0 ? archive_read_open(a, NULL, NULL, stream_read, NULL) :
+	if ((g_file_path != NULL ? archive_read_open_filename(a, g_file_path, 65536) :
+	    g_stream_blk > 0 ? archive_read_open(a, NULL, NULL, stream_read, NULL) :
 	    archive_read_open_memory(a, buf, len)) != ARCHIVE_OK) {
 		printf("{\"open\":%d,\"err\":", -30);
 		json_str(stdout, archive_error_string(a));
@@ -383,6 +385,7 @@ main(int argc, char **argv)
 		else if (!strcmp(argv[i], "--limit") && i + 1 < argc) limit = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--stream") && i + 1 < argc) g_stream_blk = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--meta")) g_meta = 1;
+		else if (!strcmp(argv[i], "--file")) g_file_path = argv[2];
 	}
 	buf = slurp(argv[2], &len);
 	if (!strcmp(argv[1], "list"))

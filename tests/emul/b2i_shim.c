@@ -53,3 +53,35 @@ int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes, const b2i_
 	return orc_decode_batch(host_in, in_bytes, (const orc_desc *)descs, n, host_out, out_bytes,
 	    (orc_stream_result *)results) == 0 ? B2I_OK : B2I_E_INVAL;
 }
+
+/* ---- what the streaming engine (csrc/b2i_pipe.cpp) and the plugins' pool need ---- */
+int b2i_device_count(void) { const char *e = getenv("B2I_SHIM_GPUS"); return e ? atoi(e) : 1; }
+int b2i_ctx_device(const b2i_ctx *c) { (void)c; return 0; }
+
+struct b2i_job {
+	b2i_ctx *c;
+	const void *in; size_t in_bytes;
+	b2i_stream_desc *descs; size_t n;
+	void *out; size_t out_bytes;
+};
+
+int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes, const b2i_stream_desc *descs, size_t n,
+    void *host_out, size_t out_bytes, b2i_job **job)
+{
+	struct b2i_job *j = calloc(1, sizeof(*j));
+	if (j == NULL)
+		return B2I_E_NOMEM;
+	j->c = c; j->in = host_in; j->in_bytes = in_bytes; j->n = n; j->out = host_out; j->out_bytes = out_bytes;
+	j->descs = malloc((n ? n : 1) * sizeof(*descs));
+	if (n) memcpy(j->descs, descs, n * sizeof(*descs));
+	*job = j;
+	return B2I_OK;
+}
+
+int b2i_wait(b2i_job *j, b2i_stream_result *res)
+{
+	int rc = j->n ? b2i_decode_host(j->c, j->in, j->in_bytes, j->descs, j->n, j->out, j->out_bytes, res) : B2I_OK;
+	free(j->descs);
+	free(j);
+	return rc;
+}

@@ -24,7 +24,7 @@ def test_abi_exports_match_header():
     for name in sorted(declared):
         assert hasattr(L, name), "header declares %s but the library does not export it" % name
     assert declared == set(capi.EXPORTS)
-    assert L.b2i_abi_version() == 3
+    assert L.b2i_abi_version() == 4
 
 
 def test_struct_layouts():
@@ -139,8 +139,38 @@ def test_plan_layout_and_partition():
     ends = sorted((int(d.out_off), int(d.out_off + d.out_cap)) for d in descs)
     assert all(a[1] <= b[0] for a, b in zip(ends, ends[1:])) and ends[-1][1] <= out_bytes
     for world in (1, 2, 3, 8):
-        w = [int(d.in_len + d.out_cap) for d in descs]
-        cuts = shard.partition_contiguous(w, world)
+        # the C partitioner of the library (b2i_partition_contiguous / b2i_partition_lpt)
+        w = [int(d.in_len + max(d.out_cap, d.expect_out)) + 1 for d in descs]
+        cuts = shard.partition_contiguous(descs, world)
         assert cuts[0][0] == 0 and cuts[-1][1] == len(w) and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
         loads = [sum(w[lo:hi]) for lo, hi in cuts]
         assert max(loads) <= sum(w) / world + max(w)
+        owner, load = capi.partition_lpt(descs, world)
+        assert sorted(set(owner)) == list(range(min(world, len(w)))) and sum(load) == sum(w)
+        assert max(load) <= sum(w) / world + max(w)
+
+
+def test_zip_index_through_fetch_callback_equals_memory_walk():
+    """File-backed sources: the index walk through bounded fetches (tail, directory, local
+    headers) gives the same entries as the walk over a memory image, for plain, ZIP64,
+    prefixed and damaged archives; the tail probe answers like the seekable bid."""
+    from libarchive_b200 import synth
+    txt = synth.synth_text(40000, 3)
+    members = [synth.ZipMember("a/%03d.txt" % i, txt[i * 90:i * 90 + 300 + 7 * i]) for i in range(120)]
+    cases = [synth.make_zip(members), synth.make_zip(members, zip64=True, framing="at_end"),
+             synth.make_zip(members[:5], prefix=b"#!/bin/sh\n" * 40, comment=b"hello")]
+    for z in cases:
+        want = capi.zip_index(z)
+        got = capi.zip_index_via_fetch(z, chunk=4096)
+        strip = lambda es: [{k: v for k, v in e.items() if k != "reserved"} for e in es]
+        assert strip(got[0]) == strip(want[0]) and got[1:3] == want[1:3]
+        assert got[3] < len(z) + 16384 + 4096 * 2          # tail + directory + headers, not the file many times over
+        tail = z[-16384:]
+        assert capi.lib().b2i_zip_probe_tail(tail, len(tail), len(z)) == 1
+    z = cases[0]
+    with pytest.raises(capi.B2IError):                       # a zeroed end record
+        capi.zip_index_via_fetch(z[:-30] + bytes(30))
+    junk = synth.synth_random(50000, 9)
+    assert capi.lib().b2i_zip_probe_tail(junk[-16384:], 16384, len(junk)) == 0
+    with pytest.raises(capi.B2IError):
+        capi.zip_index_via_fetch(junk)
