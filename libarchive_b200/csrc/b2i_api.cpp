@@ -31,7 +31,7 @@ static_assert(offsetof(b2i_stream_result, detail) == offsetof(B2iResult, detail)
 #define B2I_PIPE_SLICES  12
 
 struct b2i_plan;
-#define B2I_MAX_JOBS 2
+#define B2I_MAX_JOBS 4
 /* one host-buffer decode in flight: its own device staging, plan arena and events,
  * so that the copy-out of one job overlaps the copy-in and kernels of the next */
 struct b2i_job {
@@ -530,11 +530,14 @@ extern "C" void b2i_plan_destroy(b2i_plan *p)
 	if (p == NULL)
 		return;
 	cudaSetDevice(p->ctx->device);
-	cudaStreamSynchronize(p->stream);
 	if (p->owns_memory) {
+		cudaStreamSynchronize(p->stream);
 		cudaFree(p->d_block);
 		cudaFreeHost(p->h_block);
 	}
+	/* arena-backed plans (slices of a job) are destroyed after the job's last event has
+	 * been waited for: synchronising their compute stream here would also wait for the
+	 * OTHER jobs in flight on it and undo the overlap */
 	if (p->ev_fork) cudaEventDestroy(p->ev_fork);
 	if (p->ev_join) cudaEventDestroy(p->ev_join);
 	delete p;

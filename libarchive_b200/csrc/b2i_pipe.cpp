@@ -16,7 +16,7 @@
  *                callback sources by the CALLER's thread from inside b2i_pipe_get
  *                (libarchive's read filters may only be used on the caller's thread)
  *      decode    b2i_submit on the slot's device (H2D, kernels, D2H into the slot's
- *                pinned output buffer), two jobs in flight per device
+ *                pinned output buffer), three jobs in flight per device
  *      serve     b2i_pipe_get(i) blocks until stream i's window has landed and hands
  *                out pointers into the slot; b2i_pipe_release recycles slots
  *
@@ -275,7 +275,7 @@ static void worker_main(b2i_pipe *p, size_t dev)
 	struct Pending { size_t k; b2i_job *job; };
 	std::deque<Pending> pending;
 	size_t k = dev;
-	const size_t max_jobs = 2;
+	const size_t max_jobs = 3;
 
 	for (;;) {
 		bool started = false;
@@ -361,9 +361,19 @@ extern "C" int b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, ui
 	*out = NULL;
 	if (ctxs == NULL || nctx < 1 || (mem == NULL) == (fill == NULL) || (n && descs == NULL))
 		return B2I_E_INVAL;
-	size_t window_out = opts && opts->window_out_bytes ? opts->window_out_bytes : (size_t)64 << 20;
+	/* Windows: large enough that a device pass fills the GPU, small enough that the first
+	 * bytes arrive early and three passes overlap (copy-in, kernels, copy-out): a sixth of
+	 * the batch per device, within 16..256 MiB, unless the caller says otherwise. */
+	size_t window_out = opts && opts->window_out_bytes ? opts->window_out_bytes : 0;
+	if (window_out == 0) {
+		uint64_t total = 0;
+		for (size_t i = 0; i < n; i++)
+			total += descs[i].out_cap;
+		window_out = (size_t)std::min<uint64_t>((uint64_t)256 << 20,
+		    std::max<uint64_t>((uint64_t)16 << 20, total / (6u * (unsigned)nctx)));
+	}
 	size_t first_out = opts && opts->first_window_out_bytes ? opts->first_window_out_bytes : window_out / 4;
-	int depth = opts && opts->windows_per_device > 0 ? opts->windows_per_device : 3;
+	int depth = opts && opts->windows_per_device > 0 ? opts->windows_per_device : 4;
 	int copy_threads = opts && opts->copy_threads > 0 ? opts->copy_threads : 3;
 	if (const char *ev = getenv("B2I_PIPE_WINDOW_MB"))
 		window_out = (size_t)std::max(1, atoi(ev)) << 20, first_out = window_out / 4;

@@ -258,7 +258,13 @@ B2I_DEV void team_chunk(TeamShared *ts, unsigned w)
 			q2 = j + 2 < ntok ? rt[32u * (j + 2)] : 0;
 			q3 = j + 3 < ntok ? rt[32u * (j + 3)] : 0;
 		}
+#ifdef B2I_HOST_EMUL
+		/* the lanes do not talk to each other in this loop: under the host emulation every
+		 * lane simply runs its own (a vote per step would cost two thread barriers) */
+		while (active) {
+#else
 		while (__any_sync(B2I_FULL, active)) {
+#endif
 			if (active) {
 				uint32_t v = 0;
 				bool emit = true;

@@ -46,7 +46,7 @@ slurp(const char *path, size_t *len)
 	return buf;
 }
 
-struct pass { uint64_t bytes, entries, errors; uint32_t crc; double seconds; };
+struct pass { uint64_t bytes, entries, errors; uint32_t crc; double seconds, t_open, t_first_header, t_first_block; };
 
 static struct pass
 one_pass(const char *path, const void *buf, size_t len, int raw, int use_file, int mode_data, int check)
@@ -71,8 +71,15 @@ one_pass(const char *path, const void *buf, size_t len, int raw, int use_file, i
 		archive_read_free(a);
 		return r;
 	}
+	r.t_open = now() - t0;
 	while ((rc = archive_read_next_header(a, &e)) == ARCHIVE_OK || rc == ARCHIVE_WARN) {
+		if (r.entries == 0)
+			r.t_first_header = now() - t0;
 		r.entries++;
+		if (mode_data == 2) {
+			archive_read_data_skip(a);           /* headers only: the per-entry cost of the read core */
+			continue;
+		}
 		if (mode_data) {
 			la_ssize_t n;
 			while ((n = archive_read_data(a, out, sizeof(out))) > 0) {
@@ -87,6 +94,8 @@ one_pass(const char *path, const void *buf, size_t len, int raw, int use_file, i
 			size_t n;
 			la_int64_t off;
 			while ((rc = archive_read_data_block(a, &p, &n, &off)) == ARCHIVE_OK) {
+				if (r.bytes == 0)
+					r.t_first_block = now() - t0;
 				r.bytes += n;
 				if (check) r.crc = (uint32_t)crc32(r.crc, p, (uInt)n);
 			}
@@ -120,7 +129,10 @@ main(int argc, char **argv)
 		if (!strcmp(argv[i], "--raw")) raw = 1;
 		else if (!strcmp(argv[i], "--file")) use_file = 1;
 		else if (!strcmp(argv[i], "--check")) check = 1;
-		else if (!strcmp(argv[i], "--mode") && i + 1 < argc) mode_data = !strcmp(argv[++i], "data");
+		else if (!strcmp(argv[i], "--mode") && i + 1 < argc) {
+			i++;
+			mode_data = !strcmp(argv[i], "data") ? 1 : !strcmp(argv[i], "headers") ? 2 : 0;
+		}
 		else if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = atoi(argv[++i]);
 	}
@@ -137,10 +149,12 @@ main(int argc, char **argv)
 	}
 	printf("{\"api\":\"%s\",\"source\":\"%s\",\"steps\":%d,\"warmup\":%d,\"bytes\":%llu,\"entries\":%llu,"
 	    "\"errors\":%llu,\"seconds_mean\":%.6f,\"seconds_best\":%.6f,\"gbps_mean\":%.4f,\"crc\":\"%08x\","
+	    "\"last_pass\":{\"open_s\":%.6f,\"first_header_s\":%.6f,\"first_block_s\":%.6f,\"total_s\":%.6f},"
 	    "\"libarchive\":\"%s\"}\n",
-	    mode_data ? "archive_read_data(64KiB)" : "archive_read_data_block", use_file ? "open_filename" : "open_memory",
+	    mode_data == 1 ? "archive_read_data(64KiB)" : mode_data == 2 ? "headers only" : "archive_read_data_block",
+	    use_file ? "open_filename" : "open_memory",
 	    steps, warmup, (unsigned long long)last.bytes, (unsigned long long)last.entries,
 	    (unsigned long long)errors, steps ? sum / steps : 0, best, steps && sum > 0 ? last.bytes * steps / sum / 1e9 : 0,
-	    last.crc, archive_version_string());
+	    last.crc, last.t_open, last.t_first_header, last.t_first_block, last.seconds, archive_version_string());
 	return errors ? 1 : 0;
 }

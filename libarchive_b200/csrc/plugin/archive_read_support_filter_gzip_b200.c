@@ -46,7 +46,10 @@
 #include <stdio.h>
 
 #define OUT_BLOCK      (64 * 1024)            /* gzip.c:314 */
-#define WINDOW_TARGET  ((size_t)256 << 20)    /* decode at most this much input per device pass */
+#define WINDOW_TARGET  ((size_t)96 << 20)     /* decode at most this much input per device pass */
+#define WINDOW_READ    ((size_t)16 << 20)     /* what a block-sized source (a file) is asked to have
+                                                 buffered before a pass: one pass per 64 KiB read
+                                                 block would be one pass per three members */
 
 struct gz_b200 {
 	b2i_ctx        *ctx;
@@ -193,6 +196,14 @@ next_window(struct archive_read_filter *self)
 	b2i_gzip_member *mem = NULL;
 	size_t n = 0, end = 0, i;
 
+	/* a memory source answers with everything it has; a file source (64 KiB read blocks,
+	 * archive_read_open_filename.c:389-461) is asked to collect a window's worth first */
+	p = __archive_read_filter_ahead(up, 18, &avail);
+	if (p != NULL && avail < (ssize_t)WINDOW_READ && p[0] == 0x1f && p[1] == 0x8b && (p[3] & 4) &&
+	    p[12] == 'B' && p[13] == 'C') {
+		/* a BGZF chain (only then: a plain member is decoded from its head on demand) */
+		(void)__archive_read_filter_ahead(up, WINDOW_READ, &avail);    /* NULL: fewer bytes are left */
+	}
 	p = __archive_read_filter_ahead(up, 1, &avail);
 	if (p == NULL || avail <= 0) {
 		g->eof = 1;
@@ -267,7 +278,7 @@ next_window(struct archive_read_filter *self)
 		rc = b2i_decode_host(g->ctx, p, in_used, d, m_used, dst, out, r);
 		if (rc != B2I_OK) {
 			free(d); free(r); b2i_free(mem);
-			{ g->ctx_bad = 1; return (fatal(self, g, b2i_last_error(g->ctx))); }
+			{ g->ctx_bad = (rc == B2I_E_CUDA); return (fatal(self, g, b2i_last_error(g->ctx))); }
 		}
 		/* members are served back to back: close the 16-byte alignment gaps */
 		size_t w = 0;
@@ -349,7 +360,7 @@ next_window(struct archive_read_filter *self)
 				return (fatal(self, g, "Can't allocate data for gzip decompression"));
 			rc = b2i_decode_host(g->ctx, p, in_use, &d, 1, g->out + g->out_len, budget, &r);
 			if (rc != B2I_OK)
-				{ g->ctx_bad = 1; return (fatal(self, g, b2i_last_error(g->ctx))); }
+				{ g->ctx_bad = (rc == B2I_E_CUDA); return (fatal(self, g, b2i_last_error(g->ctx))); }
 			if (r.status == B2I_S_BUF_ERROR && in_use < (size_t)avail) {
 				in_lim *= 2;                       /* more of what is buffered */
 				continue;

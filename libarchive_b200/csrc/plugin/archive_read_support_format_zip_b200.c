@@ -304,7 +304,11 @@ zip_b200_prepare(struct archive_read *a, struct zip_b200 *z)
 		if (e->method == 0) {
 			d->flags |= B2I_F_NO_COPY;          /* served from the source bytes: zero copy */
 		} else {
-			d->out_cap = e->uncompressed_size;
+			/* deflate cannot expand by more than 1032:1 (a 258-byte match in 2 bits): a
+			 * directory that claims more gets the honest bound, not gigabytes of pinned
+			 * memory; the size check at the end of the entry still sees expect_out */
+			uint64_t bound = e->compressed_size * 1032u + 65536u;
+			d->out_cap = e->uncompressed_size < bound ? e->uncompressed_size : bound;
 			out = (out + (size_t)d->out_cap + 15) & ~(size_t)15;
 		}
 		if (d->in_off < in_lo) in_lo = d->in_off;
@@ -329,7 +333,7 @@ zip_b200_prepare(struct archive_read *a, struct zip_b200 *z)
 		}
 		if ((rc = b2i_decode_host(z->c.ctx, z->image, z->image_len, z->descs, n, z->out, out,
 		    z->res)) != B2I_OK) {
-			z->c.ctx_bad = 1;
+			z->c.ctx_bad = (rc == B2I_E_CUDA);       /* a rejected batch does not poison the context */
 			archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC, "B200 decode failed (%d): %s", rc,
 			    b2i_last_error(z->c.ctx));
 			return (ARCHIVE_FATAL);

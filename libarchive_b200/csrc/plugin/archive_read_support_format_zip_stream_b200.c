@@ -176,7 +176,7 @@ zs_decode_entry(struct archive_read *a, struct zs_b200 *z, int64_t known, int64_
 				break;
 			}
 			if ((rc = b2i_decode_host(z->c.ctx, p, in_len, &d, 1, z->out, cap, &z->res)) != B2I_OK) {
-				z->c.ctx_bad = 1;
+				z->c.ctx_bad = (rc == B2I_E_CUDA);
 				archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC, "B200 decode failed (%d): %s", rc,
 				    b2i_last_error(z->c.ctx));
 				return (ARCHIVE_FATAL);
@@ -308,7 +308,7 @@ zs_batch_decode(struct archive_read *a, struct zs_b200 *z)
 		}
 	}
 	if ((rc = b2i_decode_host(z->c.ctx, p, total, z->b.d, n, z->b.out, out, z->b.r)) != B2I_OK) {
-		z->c.ctx_bad = 1;
+		z->c.ctx_bad = (rc == B2I_E_CUDA);
 		return (0);                                     /* the plain path reports the failure */
 	}
 	z->b.n = n;

@@ -16,7 +16,9 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-REFDIR = os.path.join(ROOT, "oracle", "_ref")
+REFDIR = os.path.join(ROOT, "oracle", "_ref")               # built from the reference alone
+NEWDIR = os.path.join(ROOT, "tests", "refsuite", "_out")     # linked against this repo's modules
+DATADIR = os.path.join(ROOT, "tests", "refsuite", "testdata")  # the reference's .uu fixtures these tests name
 
 
 def list_tests(binary):
@@ -28,7 +30,7 @@ def list_tests(binary):
 def run_one(binary, test, timeout=300):
     with tempfile.TemporaryDirectory() as tmp:
         try:
-            p = subprocess.run([binary, "-r", os.path.join(REFDIR, "testdata"), "-q", test], cwd=tmp,
+            p = subprocess.run([binary, "-r", DATADIR, "-q", test], cwd=tmp,
                                capture_output=True, text=True, timeout=timeout,
                                env=dict(os.environ, TMPDIR=tmp))
         except subprocess.TimeoutExpired:
@@ -66,7 +68,7 @@ KNOWN_GAPS = {
 
 def main(argv, variant="dropin"):
     ref = os.path.join(REFDIR, "libarchive_test_ref")
-    drop = os.path.join(REFDIR, "libarchive_test_" + variant)
+    drop = os.path.join(NEWDIR, "libarchive_test_" + variant)
     only = [x for x in argv[1:] if not x.startswith("-")]
     skip = [x[1:] for x in argv[1:] if x.startswith("-")]
     tests = [t for t in list_tests(ref) if (not only or any(o in t for o in only)) and not any(k in t for k in skip)]

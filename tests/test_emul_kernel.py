@@ -107,7 +107,7 @@ def test_team_decoder_cases():
     pointer sweep, flush + history ring), stored blocks copied by the team, team CRC,
     partial regions (one segment larger than the chunk), capacity and distance errors cut
     at the exact symbol."""
-    txt = synth.synth_text(300000, 23)
+    txt = synth.synth_text(120000, 23)
 
     def team(s, cap, lead):
         buf = bytes(lead) + s
@@ -126,19 +126,19 @@ def test_team_decoder_cases():
     far = synth.deflate_raw(txt[:2000], 6)      # placeholder replaced below
     c1 = zlib.compressobj(6, zlib.DEFLATED, -15)
     far = c1.compress(txt[:2000]) + c1.flush(zlib.Z_FULL_FLUSH) + co.compress(far_body) + co.flush()
-    mixed = synth.deflate_mixed([(txt[:100000], 6, zlib.Z_DEFAULT_STRATEGY),
+    mixed = synth.deflate_mixed([(txt[:50000], 6, zlib.Z_DEFAULT_STRATEGY),
                                  (synth.synth_random(70000, 3), 6, zlib.Z_DEFAULT_STRATEGY),
-                                 (txt[100000:200000], 1, zlib.Z_FIXED)])
+                                 (txt[50000:100000], 1, zlib.Z_FIXED)])
     cases = [("text", full, 1 << 19, 9), ("small", synth.deflate_raw(txt[:14000], 6), 1 << 15, 3),
-             ("truncated", full[:50000], 1 << 19, 0), ("cap", full, 123457, 5),
-             ("fixed", synth.deflate_raw(txt[:200000], 1, zlib.Z_FIXED), 1 << 18, 1),
+             ("truncated", full[:25000], 1 << 19, 0), ("cap", full, 63457, 5),
+             ("fixed", synth.deflate_raw(txt[:70000], 1, zlib.Z_FIXED), 1 << 18, 1),
              ("stored-blocks", synth.deflate_raw(synth.synth_random(200000, 5), 6), 1 << 18, 7),
              # n = 8 * 16 * k + 3: the eight CRC slices must still cover the last bytes
              ("crc-slices", synth.deflate_raw(synth.synth_random(8 * 16 * 600 + 3, 6), 6), 1 << 17, 6),
              ("mixed", mixed, 1 << 19, 11),
-             ("rle", synth.deflate_raw((b"ab" * 50000 + txt[:5000]) * 6, 6), 1 << 20, 2),
-             ("zeros", synth.deflate_raw(bytes(8 << 20), 6), 9 << 20, 13),
-             ("zeros-cap", synth.deflate_raw(bytes(8 << 20), 6), (8 << 20) - 100001, 13),
+             ("rle", synth.deflate_raw((b"ab" * 50000 + txt[:5000]) * 2, 6), 1 << 20, 2),
+             ("zeros", synth.deflate_raw(bytes(5 << 20), 6), 6 << 20, 13),
+             ("zeros-cap", synth.deflate_raw(bytes(5 << 20), 6), (5 << 20) - 100001, 13),
              ("far-mid-stream", far, 1 << 17, 4)]
     for name, s, cap, lead in cases:
         o, od = ob.inflate(s, cap)

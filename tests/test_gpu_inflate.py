@@ -316,8 +316,13 @@ def test_two_jobs_in_flight(ctx):
         C.memmove(h_in, z, len(z))
         batches.append((z, descs, out_bytes, h_in, h_out))
     jobs = [ctx.submit(b[3], len(b[0]), b[1], b[4], b[2]) for b in batches[:2]]
+    # four jobs may be in flight on one context; a fifth is refused
+    extra = [ctx.submit(batches[2][3], len(batches[2][0]), batches[2][1], batches[2][4], batches[2][2])
+             for _ in range(2)]
     with pytest.raises(capi.B2IError):
         ctx.submit(batches[2][3], len(batches[2][0]), batches[2][1], batches[2][4], batches[2][2])
+    for j in extra:
+        ctx.wait(j)
     results = [ctx.wait(jobs[0])]
     jobs.append(ctx.submit(batches[2][3], len(batches[2][0]), batches[2][1], batches[2][4], batches[2][2]))
     results += [ctx.wait(jobs[1]), ctx.wait(jobs[2])]

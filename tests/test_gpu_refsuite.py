@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "refsuite"))
-from run_refsuite import KNOWN_GAPS, REFDIR  # noqa: E402
+from run_refsuite import KNOWN_GAPS, NEWDIR, REFDIR  # noqa: E402
 from test_refsuite_hostlogic import run_all  # noqa: E402
 from libarchive_b200 import synth  # noqa: E402
 
@@ -21,9 +21,9 @@ pytestmark = pytest.mark.gpu
 
 
 def need(name):
-    path = os.path.join(REFDIR, name)
+    path = os.path.join(NEWDIR if name.endswith("_dropin") else REFDIR, name)
     if not os.path.exists(path):
-        pytest.skip("oracle/_ref/%s not built (needs /root/reference at build time)" % name)
+        pytest.skip("%s not built (needs /root/reference at build time)" % name)
     return path
 
 

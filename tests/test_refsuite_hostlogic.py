@@ -17,11 +17,11 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "refsuite"))
-from run_refsuite import KNOWN_GAPS, REFDIR  # noqa: E402
+from run_refsuite import DATADIR, KNOWN_GAPS, NEWDIR, REFDIR  # noqa: E402
 
 
 def run_all(binary, tmp_path, timeout):
-    p = subprocess.run([binary, "-q", "-r", os.path.join(REFDIR, "testdata")], cwd=tmp_path, capture_output=True,
+    p = subprocess.run([binary, "-q", "-r", DATADIR], cwd=tmp_path, capture_output=True,
                        text=True, errors="replace", timeout=timeout, env=dict(os.environ, TMPDIR=str(tmp_path)))
     text = p.stdout + p.stderr
     failing = set(re.findall(r"^\s*\d+: (\S+) \(\d+ failures\)", text, re.M))
@@ -32,9 +32,9 @@ def run_all(binary, tmp_path, timeout):
 
 
 def test_reference_tests_pass_on_plugin_host_logic(tmp_path):
-    binary = os.path.join(REFDIR, "libarchive_test_hostlogic")
+    binary = os.path.join(NEWDIR, "libarchive_test_hostlogic")
     if not os.path.exists(binary):
-        pytest.skip("oracle/_ref/libarchive_test_hostlogic not built (needs /root/reference)")
+        pytest.skip("tests/refsuite/_out/libarchive_test_hostlogic not built (needs /root/reference)")
     rc, n, failing, text = run_all(binary, tmp_path, 900)
     assert rc >= 0, "the test runner crashed:\n" + text[-2000:]
     assert n >= 125, text[-2000:]
@@ -46,7 +46,7 @@ def test_streaming_reader_reports_match_reference():
     """Generated archives read through a read callback only (no seeking): the streaming reader's
     host logic against the unmodified reference - good entries, data descriptors, bad CRC, wrong
     sizes, junk after the stream, invalid block type, truncation."""
-    ref, new = os.path.join(REFDIR, "oracle_extract"), os.path.join(REFDIR, "hostlogic_extract")
+    ref, new = os.path.join(REFDIR, "oracle_extract"), os.path.join(NEWDIR, "hostlogic_extract")
     if not (os.path.exists(ref) and os.path.exists(new)):
         pytest.skip("oracle/_ref drivers not built (needs /root/reference)")
     sys.path.insert(0, ROOT)
@@ -59,7 +59,7 @@ def test_reference_fixtures_full_metadata_match_reference():
     """All reference fixtures, seekable and streamed, including owner / access and change times /
     link targets / encryption flags (the extra fields 0x5455, 0x5855, 0x7855, 0x7875, 0x7075)."""
     import json
-    ref, new = os.path.join(REFDIR, "oracle_extract"), os.path.join(REFDIR, "hostlogic_extract")
+    ref, new = os.path.join(REFDIR, "oracle_extract"), os.path.join(NEWDIR, "hostlogic_extract")
     if not (os.path.exists(ref) and os.path.exists(new)):
         pytest.skip("oracle/_ref drivers not built (needs /root/reference)")
     sys.path.insert(0, ROOT)
