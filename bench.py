@@ -19,8 +19,9 @@ entry inflated and CRC-32 verified in ONE device pass per step.
   configs    configs 2-5 (stored1m / bgzf64k / mixed / tiny4k): device-resident GB/s,
              roofline fraction, C-ABI e2e and a CPU baseline each (sizes: see `scale`;
              --full runs the BASELINE sizes)
-  strong     (N > 1) ONE archive of configs 3, 4, 5 split over the N ranks by the
-             library's partitioner (b2i_partition_contiguous / _lpt), device-resident
+  strong     ONE archive of configs 3, 5 (full size) and 4 (half size) split over the N
+             ranks by the library's partitioner (b2i_partition_contiguous / _lpt),
+             device-resident; N = 1 is the base of the series
   cpu_baseline  the reference's own CPU path (oracle/_ref: unmodified libarchive + zlib)
              on the box's host cores, bounded sample
 
@@ -527,20 +528,24 @@ def strong_scaling(rig, name, scale, rank, K, W):
     """ONE archive split over the ranks by the library's partitioner; device-resident."""
     from libarchive_b200 import shard
     capi, L, ctx = rig.capi, rig.L, rig.ctx
-    path = "/dev/shm/b2i_strong_%s_%d.bin" % (name, os.getppid())
-    if rank == 0:
+    if rig.world == 1:
         archive, kind = build_workload(name, 0, scale)
-        with open(path + ".tmp", "wb") as f:
-            f.write(archive)
-        os.rename(path + ".tmp", path)
-    rig.barrier()
-    if rank != 0:
-        with open(path, "rb") as f:
-            archive = f.read()
-        kind = CONFIGS[name][1]
-    rig.barrier()
-    if rank == 0:
-        os.unlink(path)
+    else:
+        # rank 0 builds the archive once; the others read it from shared memory
+        path = "/dev/shm/b2i_strong_%s_%d.bin" % (name, os.getppid())
+        if rank == 0:
+            archive, kind = build_workload(name, 0, scale)
+            with open(path + ".tmp", "wb") as f:
+                f.write(archive)
+            os.rename(path + ".tmp", path)
+        rig.barrier()
+        if rank != 0:
+            with open(path, "rb") as f:
+                archive = f.read()
+            kind = CONFIGS[name][1]
+        rig.barrier()
+        if rank == 0:
+            os.unlink(path)
     descs, out_bytes, usize, csize = plan_for(archive, kind)
     lpt = name == "mixed"
     if lpt:
@@ -741,12 +746,16 @@ def main():
             except SystemExit as ex:
                 configs[name] = {"error": str(ex)}
         line["configs"] = configs
-        if world > 1:
-            strong = {}
-            for name in ("bgzf64k", "mixed", "tiny4k"):
-                note("strong %s" % name)
-                strong[name] = strong_scaling(rig, name, scale_of(name), rank, Kc, Wc)
-            line["strong"] = strong
+        # ONE archive split over the N ranks (N = 1: the whole of it, the base of the series);
+        # large enough that a rank's share still fills its GPU at N = 8
+        strong = {}
+        for name, sc in (("bgzf64k", 1.0), ("tiny4k", 1.0), ("mixed", 0.5)):
+            note("strong %s" % name)
+            try:
+                strong[name] = strong_scaling(rig, name, sc, rank, Kc, Wc)
+            except SystemExit as ex:
+                strong[name] = {"error": str(ex)}
+        line["strong"] = strong
 
     if rank == 0:
         print(json.dumps(line))

@@ -197,7 +197,7 @@ typedef struct b2i_pipe_opts {
 	size_t window_out_bytes;        /* 0: a sixth of the batch's output, 16..256 MiB */
 	size_t first_window_out_bytes;  /* 0: a quarter of that (first bytes arrive sooner) */
 	int    windows_per_device;      /* ring depth, 0: 4 (three of them in flight) */
-	int    copy_threads;            /* staging threads for pageable memory, 0: 3 */
+	int    copy_threads;            /* staging threads for pageable memory, 0: 6 */
 } b2i_pipe_opts;
 int  b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, uint64_t mem_size,
                    b2i_fill_fn fill, void *user, const b2i_stream_desc *descs, size_t n,

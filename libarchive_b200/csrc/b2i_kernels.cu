@@ -28,6 +28,7 @@
 #else
 #define INFLATE_CTAS 7
 #endif
+#define TEAM_CTAS_PER_SM (TEAM_WARPS >= 16 ? 1 : 2)
 #define INFLATE_SLOTS 64u      /* token regions per SM: twice the resident warps of the larger build */
 
 #if defined(B2I_PHASE_CLOCKS) && !defined(B2I_R9)
@@ -99,7 +100,7 @@ b2i_inflate_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *_
  * Warp 0 pulls streams from the counter and owns them; the other warps serve its
  * PASS / RESOLVE commands until it quits.
  */
-extern "C" __global__ void __launch_bounds__(TEAM_LANES, 2)
+extern "C" __global__ void __launch_bounds__(TEAM_LANES, TEAM_CTAS_PER_SM)
 b2i_inflate_team_kernel(const uint8_t *__restrict__ in, uint64_t in_total, uint8_t *__restrict__ out,
     uint8_t *__restrict__ out_mirror,
     const B2iDesc *__restrict__ descs, B2iResult *__restrict__ results,
@@ -432,7 +433,7 @@ cudaError_t b2i_launch_inflate_team(const uint8_t *in, uint64_t in_total, uint8_
     unsigned int *slot_busy, int num_sms, cudaStream_t st)
 {
 	const size_t smem = sizeof(WarpSmem) + sizeof(TeamShared);
-	uint32_t blocks = n < (uint32_t)num_sms * 2u ? n : (uint32_t)num_sms * 2u;
+	uint32_t blocks = n < (uint32_t)num_sms * TEAM_CTAS_PER_SM ? n : (uint32_t)num_sms * TEAM_CTAS_PER_SM;
 	b2i_inflate_team_kernel<<<blocks, TEAM_LANES, smem, st>>>(in, in_total, out, out_mirror, descs,
 	    results, order, n, counter, crc_tab, xp8, scratch, slot_busy, b2i_inflate_scratch_slots(num_sms));
 	return cudaGetLastError();

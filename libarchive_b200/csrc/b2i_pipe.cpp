@@ -374,7 +374,7 @@ extern "C" int b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, ui
 	}
 	size_t first_out = opts && opts->first_window_out_bytes ? opts->first_window_out_bytes : window_out / 4;
 	int depth = opts && opts->windows_per_device > 0 ? opts->windows_per_device : 4;
-	int copy_threads = opts && opts->copy_threads > 0 ? opts->copy_threads : 3;
+	int copy_threads = opts && opts->copy_threads > 0 ? opts->copy_threads : 6;
 	if (const char *ev = getenv("B2I_PIPE_WINDOW_MB"))
 		window_out = (size_t)std::max(1, atoi(ev)) << 20, first_out = window_out / 4;
 

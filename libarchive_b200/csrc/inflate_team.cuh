@@ -46,11 +46,15 @@
  */
 #pragma once
 
-#define TEAM_WARPS    8
+#ifndef TEAM_WARPS
+#define TEAM_WARPS    16                    /* one CTA per SM: all of its warps on ONE stream */
+#endif
 #define TEAM_LANES    (32 * TEAM_WARPS)
 #define TEAM_SEG_MAX  1024u                 /* bits per lane and round, at most */
 #define TEAM_MIN_BITS ((uint64_t)TEAM_LANES * LP_SEG_MIN)
-#define TEAM_CHUNK    28672u                /* 16-bit symbols in the chunk buffer */
+#ifndef TEAM_CHUNK
+#define TEAM_CHUNK    (3584u * TEAM_WARPS)  /* 16-bit symbols in the chunk buffer (112 KB for 16 warps) */
+#endif
 #define TEAM_HIST     32768u                /* history ring: the deflate window */
 #define TEAM_SEG_INIT 288u                  /* first round: assume 3:1 */
 
@@ -61,7 +65,10 @@
 #define TC_COPY      5u
 #define TC_CRC       6u
 
-#define TS_PTR       0x8000u                /* symbol is a pointer to chunk index (s & 0x7fff) */
+/* a symbol is a byte (< 256) or 256 + the chunk index it points at (TEAM_CHUNK + 256 <= 65536) */
+#define TS_IS_PTR(s)  ((s) >= 256u)
+#define TS_MAKE(q)    ((q) + 256u)
+#define TS_INDEX(s)   ((s) - 256u)
 #define TEAM_NOERR   0xffffffffu
 
 struct __align__(16) TeamShared {
@@ -307,7 +314,7 @@ B2I_DEV void team_chunk(TeamShared *ts, unsigned w)
 							const uint32_t p = pos + k;
 							if (k < nn) {
 								B2I_CHECK(p < TEAM_CHUNK);
-								ts->sym[p] = (uint16_t)(p >= d + lead ? (TS_PTR | (p - d))
+								ts->sym[p] = (uint16_t)(p >= d + lead ? TS_MAKE(p - d)
 								    : (uint32_t)ts->hist[(abs0 + (p - lead) - d) & (TEAM_HIST - 1)]);
 							}
 						}
@@ -346,11 +353,11 @@ B2I_DEV void team_chunk(TeamShared *ts, unsigned w)
 			if (i + 1 < lead || i + 1 >= end) b = 0;
 			if (i + 2 < lead || i + 2 >= end) c = 0;
 			if (i + 3 < lead || i + 3 >= end) e = 0;
-			while ((a | b | c | e) & TS_PTR) {
-				if (a & TS_PTR) a = ts->sym[a & 0x7fffu];
-				if (b & TS_PTR) b = ts->sym[b & 0x7fffu];
-				if (c & TS_PTR) c = ts->sym[c & 0x7fffu];
-				if (e & TS_PTR) e = ts->sym[e & 0x7fffu];
+			while ((a | b | c | e) >= 256u) {
+				if (TS_IS_PTR(a)) a = ts->sym[TS_INDEX(a)];
+				if (TS_IS_PTR(b)) b = ts->sym[TS_INDEX(b)];
+				if (TS_IS_PTR(c)) c = ts->sym[TS_INDEX(c)];
+				if (TS_IS_PTR(e)) e = ts->sym[TS_INDEX(e)];
 			}
 			v.x = a | (b << 16);
 			v.y = c | (e << 16);
@@ -447,7 +454,7 @@ B2I_DEV void team_crc(TeamShared *ts, unsigned w)
 		tab[i] = ts->crc_tab_g[i];
 	team_sync();
 	const uint64_t n = ts->crc_n;
-	const uint64_t slice = (((n + TEAM_WARPS - 1) / TEAM_WARPS) + 15) & ~(uint64_t)15;     /* 8 slices cover n */
+	const uint64_t slice = (((n + TEAM_WARPS - 1) / TEAM_WARPS) + 15) & ~(uint64_t)15;     /* the slices cover n */
 	const uint64_t lo = (uint64_t)w * slice < n ? (uint64_t)w * slice : n;
 	const uint64_t hi = lo + slice < n ? lo + slice : n;
 	uint32_t raw0 = crc_warp_raw0(ts->crc_p + lo, hi - lo, tab, ts->crc_xp8);
