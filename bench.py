@@ -749,7 +749,7 @@ def main():
         # ONE archive split over the N ranks (N = 1: the whole of it, the base of the series);
         # large enough that a rank's share still fills its GPU at N = 8
         strong = {}
-        for name, sc in (("bgzf64k", 1.0), ("tiny4k", 1.0), ("mixed", 0.5)):
+        for name, sc in (() if args.full and world == 1 else (("bgzf64k", 1.0), ("tiny4k", 1.0), ("mixed", 0.5))):
             note("strong %s" % name)
             try:
                 strong[name] = strong_scaling(rig, name, sc, rank, Kc, Wc)

@@ -27,11 +27,13 @@ static_assert(offsetof(b2i_stream_result, detail) == offsetof(B2iResult, detail)
 
 /* per-stream limits of this build: 32-bit positions inside one stream */
 #define B2I_MAX_STREAM_BYTES 0xFFFF0000ull
-#define B2I_PIPE_STREAMS 4
+#define B2I_MAX_JOBS_ 4
+#define B2I_PIPE_STREAMS (B2I_MAX_JOBS_ * B2I_PIPE_SLICES)   /* compute streams: every slice of every job in flight its own */
 #define B2I_PIPE_SLICES  12
+#define B2I_TEAM_STREAMS (B2I_MAX_JOBS_ * B2I_PIPE_SLICES)
 
 struct b2i_plan;
-#define B2I_MAX_JOBS 4
+#define B2I_MAX_JOBS B2I_MAX_JOBS_
 /* one host-buffer decode in flight: its own device staging, plan arena and events,
  * so that the copy-out of one job overlaps the copy-in and kernels of the next */
 struct b2i_job {
@@ -63,8 +65,9 @@ struct b2i_ctx {
 	/* pipelined host path: copy-in / compute / copy-out streams, and a reusable
 	 * (grow-only) arena for the slice plans so that no call allocates */
 	cudaStream_t s_in, s_out, s_cmp[B2I_PIPE_STREAMS];
-	cudaStream_t s_team[B2I_PIPE_STREAMS];   /* large streams (one CTA each) run beside the single-warp kernel,
-	                                           one team stream per compute stream so that slices overlap */
+	cudaStream_t s_team[B2I_TEAM_STREAMS];   /* large streams (one CTA each) run beside the single-warp kernel;
+	                                           every slice of every job in flight gets its own, so that a
+	                                           slice's long CTAs never queue behind another slice's */
 	cudaEvent_t ev_free;
 	bool pipe_ready;
 	b2i_job jobs[B2I_MAX_JOBS];     /* host-buffer decodes in flight (b2i_submit / b2i_wait) */
@@ -96,6 +99,7 @@ struct b2i_plan {
 	bool owns_memory;        /* false: d_block / h_block live in the context's arena */
 	uint8_t *out_mirror;     /* host-mapped twin of the output (inflated bytes are stored to both) */
 	size_t batch_streams;    /* deflate streams of the whole batch this plan is a slice of (0: just this plan) */
+	bool defer_join;         /* the caller orders its consumers behind ev_join itself (pipelined slices) */
 };
 
 static int fail(b2i_ctx *c, int code, const char *fmt, ...)
@@ -200,7 +204,7 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 			cudaEventDestroy(J->ev_done);
 		}
 	}
-	for (int i = 0; i < B2I_PIPE_STREAMS; i++)
+	for (int i = 0; i < B2I_TEAM_STREAMS; i++)
 		if (c->s_team[i]) cudaStreamDestroy(c->s_team[i]);
 	if (c->pipe_ready) {
 		cudaStreamDestroy(c->s_in);
@@ -408,7 +412,7 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 	p->d_results = (B2iResult *)(p->d_block + o_results);
 
 	if (!big.empty()) {
-		team_lane %= B2I_PIPE_STREAMS;
+		team_lane = (int)((unsigned)team_lane % B2I_TEAM_STREAMS);
 		if (c->s_team[team_lane] == NULL &&
 		    cudaStreamCreateWithFlags(&c->s_team[team_lane], cudaStreamNonBlocking) != cudaSuccess) {
 			b2i_plan_destroy(p);
@@ -506,8 +510,11 @@ extern "C" int b2i_plan_launch(b2i_plan *p, const void *d_in, size_t in_bytes, v
 		CU(c, b2i_launch_unsupported(p->d_descs, p->d_results, p->d_unsup, p->n_unsup, p->stream));
 		c->launches++;
 	}
-	if (p->n_big)
-		CU(c, cudaStreamWaitEvent(p->stream, p->ev_join, 0));      /* join */
+	/* join: the plan's stream waits for the team kernel - unless the caller takes care of
+	 * that (a pipelined slice orders only its copy-out behind it, so that the compute
+	 * stream is not held up for as long as the slice's largest stream takes) */
+	if (p->n_big && !p->defer_join)
+		CU(c, cudaStreamWaitEvent(p->stream, p->ev_join, 0));
 	return B2I_OK;
 }
 
@@ -742,14 +749,14 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 	for (size_t s = 0; s < K && rc == B2I_OK; s++) {
 		const b2i_stream_desc *sd = descs + cut[s];
 		const size_t sn = cut[s + 1] - cut[s];
-		cudaStream_t cs = c->s_cmp[s % B2I_PIPE_STREAMS];
+		cudaStream_t cs = c->s_cmp[((size_t)(J - c->jobs) * B2I_PIPE_SLICES + s) % B2I_PIPE_STREAMS];
 		if (sn == 0)
 			continue;
 		/* copy-in stream, in order: this slice's plan block, then its bytes.  (Copies
 		 * of one direction execute in submission order, so the small plan upload
 		 * must not queue behind later slices' data.) */
 		rc = b2i_plan_build(c, sd, sn, cs, c->s_in, J->arena_d + arena_off[s], J->arena_h + arena_off[s],
-		    align_up(plan_block_bound(sn, stored_bytes), 256), &plans[s], (int)(s % B2I_PIPE_STREAMS));
+		    align_up(plan_block_bound(sn, stored_bytes), 256), &plans[s], (int)((J - c->jobs) * B2I_PIPE_SLICES + s));
 		if (rc != B2I_OK)
 			break;
 		/* the slice's input: runs of streams that follow each other in the source (one run
@@ -787,11 +794,13 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		}
 		plans[s]->out_mirror = mirror;
 		plans[s]->batch_streams = n;
+		plans[s]->defer_join = true;
 		rc = b2i_plan_launch(plans[s], J->d_in, in_bytes, J->d_out, out_bytes);
 		if (rc != B2I_OK)
 			break;
 		if (cudaEventRecord(J->ev_k[s], cs) != cudaSuccess ||
-		    cudaStreamWaitEvent(c->s_out, J->ev_k[s], 0) != cudaSuccess) {
+		    cudaStreamWaitEvent(c->s_out, J->ev_k[s], 0) != cudaSuccess ||
+		    (plans[s]->n_big && cudaStreamWaitEvent(c->s_out, plans[s]->ev_join, 0) != cudaSuccess)) {
 			rc = fail(c, B2I_E_CUDA, "event"); break;
 		}
 		/* copy-out stream, in order: the slice's decoded bytes, then its results */

@@ -343,25 +343,30 @@ B2I_DEV void team_chunk(TeamShared *ts, unsigned w)
 	const uint32_t end = lead + T;
 	{
 		const uint32_t slice = (((end + TEAM_WARPS - 1) / TEAM_WARPS) + 127u) & ~127u;
-		uint32_t i = w * slice + 4u * lane;
 		const uint32_t stop_at = (w + 1) * slice < end ? (w + 1) * slice : end;
-		for (; i < stop_at; i += 128) {
-			uint2 v = *(const uint2 *)&ts->sym[i];
-			uint32_t a = v.x & 0xffffu, b = v.x >> 16, c = v.y & 0xffffu, e = v.y >> 16;
-			/* symbols in front of the chunk's first byte or past its end are not ours */
-			if (i < lead) a = 0;
-			if (i + 1 < lead || i + 1 >= end) b = 0;
-			if (i + 2 < lead || i + 2 >= end) c = 0;
-			if (i + 3 < lead || i + 3 >= end) e = 0;
-			while ((a | b | c | e) >= 256u) {
-				if (TS_IS_PTR(a)) a = ts->sym[TS_INDEX(a)];
-				if (TS_IS_PTR(b)) b = ts->sym[TS_INDEX(b)];
-				if (TS_IS_PTR(c)) c = ts->sym[TS_INDEX(c)];
-				if (TS_IS_PTR(e)) e = ts->sym[TS_INDEX(e)];
+		for (uint32_t base = w * slice; base < stop_at; base += 128) {
+			const uint32_t i = base + 4u * lane;
+			if (i < stop_at) {
+				uint2 v = *(const uint2 *)&ts->sym[i];
+				uint32_t a = v.x & 0xffffu, b = v.x >> 16, c = v.y & 0xffffu, e = v.y >> 16;
+				/* symbols in front of the chunk's first byte or past its end are not ours */
+				if (i < lead) a = 0;
+				if (i + 1 < lead || i + 1 >= end) b = 0;
+				if (i + 2 < lead || i + 2 >= end) c = 0;
+				if (i + 3 < lead || i + 3 >= end) e = 0;
+				while ((a | b | c | e) >= 256u) {
+					if (TS_IS_PTR(a)) a = ts->sym[TS_INDEX(a)];
+					if (TS_IS_PTR(b)) b = ts->sym[TS_INDEX(b)];
+					if (TS_IS_PTR(c)) c = ts->sym[TS_INDEX(c)];
+					if (TS_IS_PTR(e)) e = ts->sym[TS_INDEX(e)];
+				}
+				v.x = a | (b << 16);
+				v.y = c | (e << 16);
+				*(uint2 *)&ts->sym[i] = v;
 			}
-			v.x = a | (b << 16);
-			v.y = c | (e << 16);
-			*(uint2 *)&ts->sym[i] = v;
+			/* the lanes stay together: everything below `base` is bytes by now, so a chain
+			 * ends after a few hops whatever the distances are */
+			__syncwarp();
 		}
 	}
 	team_sync();
