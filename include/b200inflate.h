@@ -157,8 +157,8 @@ int  b2i_decode_host(b2i_ctx *, const void *host_in, size_t in_bytes,
  * one archive in pieces) keeps the device and both directions of the host link
  * busy: b2i_submit queues copy-in, kernels and copy-out and returns; b2i_wait
  * blocks until the job's last byte has landed in host_out, fills res[n] and
- * releases the job.  Up to four jobs of one context may be in flight, so the
- * copy-out of one overlaps the copy-in and decode of the next ones; a fifth submit
+ * releases the job.  Up to five jobs of one context may be in flight, so the
+ * copy-out of one overlaps the copy-in and decode of the next ones; a sixth submit
  * fails with B2I_E_INVAL.  The descriptors are copied by b2i_submit; host_in and
  * host_out must stay valid (and should be pinned, b2i_host_alloc) until b2i_wait
  * returns.  Replaces the reference's one-entry-at-a-time inflate loop
@@ -185,7 +185,7 @@ int  b2i_decode_host_multi(b2i_ctx *const *ctxs, int nctx, const void *host_in, 
  * 431-511) for a whole archive: the descriptors (in_off = offset in the SOURCE,
  * out_off ignored, archive order) are cut into windows of bounded output; windows are
  * staged through a ring of pinned buffers, decoded round-robin by the given contexts
- * (one worker thread and three jobs in flight per GPU) and handed out in order.
+ * (one worker thread and four jobs in flight per GPU) and handed out in order.
  * Resident memory is windows_per_device x nctx x (window input + output), whatever
  * the archive size.  Source: `mem` (the archive image in host memory: staged by copy
  * threads, or used in place when it is pinned) or `fill` (called ONLY on the thread
@@ -194,9 +194,10 @@ int  b2i_decode_host_multi(b2i_ctx *const *ctxs, int nctx, const void *host_in, 
 typedef int (*b2i_fill_fn)(void *user, uint64_t offset, uint64_t len, void *dst);
 typedef struct b2i_pipe b2i_pipe;
 typedef struct b2i_pipe_opts {
-	size_t window_out_bytes;        /* 0: a sixth of the batch's output, 16..256 MiB */
+	size_t window_out_bytes;        /* 0: a quarter of the batch's output per device, 16..256 MiB
+	                                   (callback sources: at most 64 MiB) */
 	size_t first_window_out_bytes;  /* 0: a quarter of that (first bytes arrive sooner) */
-	int    windows_per_device;      /* ring depth, 0: 4 (three of them in flight) */
+	int    windows_per_device;      /* ring depth, 0: 5 (four of them in flight) */
 	int    copy_threads;            /* staging threads for pageable memory, 0: 6 */
 } b2i_pipe_opts;
 int  b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, uint64_t mem_size,

@@ -27,7 +27,7 @@ static_assert(offsetof(b2i_stream_result, detail) == offsetof(B2iResult, detail)
 
 /* per-stream limits of this build: 32-bit positions inside one stream */
 #define B2I_MAX_STREAM_BYTES 0xFFFF0000ull
-#define B2I_MAX_JOBS_ 4
+#define B2I_MAX_JOBS_ 5
 #define B2I_PIPE_STREAMS (B2I_MAX_JOBS_ * B2I_PIPE_SLICES)   /* compute streams: every slice of every job in flight its own */
 #define B2I_PIPE_SLICES  12
 #define B2I_TEAM_STREAMS (B2I_MAX_JOBS_ * B2I_PIPE_SLICES)

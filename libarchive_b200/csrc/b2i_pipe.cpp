@@ -16,7 +16,7 @@
  *                callback sources by the CALLER's thread from inside b2i_pipe_get
  *                (libarchive's read filters may only be used on the caller's thread)
  *      decode    b2i_submit on the slot's device (H2D, kernels, D2H into the slot's
- *                pinned output buffer), three jobs in flight per device
+ *                pinned output buffer), four jobs in flight per device
  *      serve     b2i_pipe_get(i) blocks until stream i's window has landed and hands
  *                out pointers into the slot; b2i_pipe_release recycles slots
  *
@@ -209,6 +209,7 @@ struct b2i_pipe {
 	int error = B2I_OK;
 	char err[256] = {0};
 	uint64_t stat_windows = 0, stat_fill_ns = 0;
+	size_t max_jobs = 4;         /* device passes in flight per GPU */
 
 	size_t window_of(size_t idx) const
 	{
@@ -275,7 +276,7 @@ static void worker_main(b2i_pipe *p, size_t dev)
 	struct Pending { size_t k; b2i_job *job; };
 	std::deque<Pending> pending;
 	size_t k = dev;
-	const size_t max_jobs = 3;
+	const size_t max_jobs = p->max_jobs;
 
 	for (;;) {
 		bool started = false;
@@ -369,19 +370,34 @@ extern "C" int b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, ui
 		uint64_t total = 0;
 		for (size_t i = 0; i < n; i++)
 			total += descs[i].out_cap;
+		/* memory sources: a quarter of the batch per device, 16..256 MiB (four passes in
+		 * flight fill the GPU: measured on config 1 through the public API, 22 -> 28 GB/s
+		 * against 43 MiB windows and three passes).  Callback sources are bounded by the
+		 * caller's thread reading and copying (a few GB/s): 64 MiB windows keep the pinned
+		 * ring - which costs seconds to pin per GiB in a cold process - small. */
 		window_out = (size_t)std::min<uint64_t>((uint64_t)256 << 20,
-		    std::max<uint64_t>((uint64_t)16 << 20, total / (6u * (unsigned)nctx)));
+		    std::max<uint64_t>((uint64_t)16 << 20, total / (4u * (unsigned)nctx)));
+		if (fill != NULL && window_out > ((size_t)64 << 20))
+			window_out = (size_t)64 << 20;
 	}
 	size_t first_out = opts && opts->first_window_out_bytes ? opts->first_window_out_bytes : window_out / 4;
-	int depth = opts && opts->windows_per_device > 0 ? opts->windows_per_device : 4;
+	int depth = opts && opts->windows_per_device > 0 ? opts->windows_per_device : 5;
 	int copy_threads = opts && opts->copy_threads > 0 ? opts->copy_threads : 6;
 	if (const char *ev = getenv("B2I_PIPE_WINDOW_MB"))
 		window_out = (size_t)std::max(1, atoi(ev)) << 20, first_out = window_out / 4;
+	if (const char *ev = getenv("B2I_PIPE_FIRST_MB"))
+		first_out = (size_t)std::max(1, atoi(ev)) << 20;
+	if (const char *ev = getenv("B2I_PIPE_DEPTH"))
+		depth = std::max(2, atoi(ev));
+	size_t jobs = 4;
+	if (const char *ev = getenv("B2I_PIPE_JOBS"))
+		jobs = (size_t)std::min(4, std::max(1, atoi(ev)));
 
 	b2i_pipe *p = new (std::nothrow) b2i_pipe();
 	if (p == NULL)
 		return B2I_E_NOMEM;
 	p->ctxs.assign(ctxs, ctxs + nctx);
+	p->max_jobs = jobs;
 	p->mem = (const uint8_t *)mem;
 	p->mem_size = mem_size;
 	p->fill = fill;

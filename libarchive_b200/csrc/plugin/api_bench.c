@@ -111,6 +111,25 @@ one_pass(const char *path, const void *buf, size_t len, int raw, int use_file, i
 	return r;
 }
 
+/* peak and current resident memory of this process, from /proc/self/status (kB) */
+static void
+mem_status(long *hwm, long *anon, long *file, long *shmem)
+{
+	FILE *f = fopen("/proc/self/status", "r");
+	char line[256];
+
+	*hwm = *anon = *file = *shmem = -1;
+	if (f == NULL)
+		return;
+	while (fgets(line, sizeof(line), f) != NULL) {
+		sscanf(line, "VmHWM: %ld", hwm);
+		sscanf(line, "RssAnon: %ld", anon);
+		sscanf(line, "RssFile: %ld", file);
+		sscanf(line, "RssShmem: %ld", shmem);
+	}
+	fclose(f);
+}
+
 int
 main(int argc, char **argv)
 {
@@ -147,7 +166,10 @@ main(int argc, char **argv)
 		}
 		last = r;
 	}
-	printf("{\"api\":\"%s\",\"source\":\"%s\",\"steps\":%d,\"warmup\":%d,\"bytes\":%llu,\"entries\":%llu,"
+	long hwm, anon, filek, shmem;
+	mem_status(&hwm, &anon, &filek, &shmem);
+	printf("{\"vm_hwm_kb\":%ld,\"rss_anon_kb\":%ld,\"rss_file_kb\":%ld,\"rss_shmem_kb\":%ld,", hwm, anon, filek, shmem);
+	printf("\"api\":\"%s\",\"source\":\"%s\",\"steps\":%d,\"warmup\":%d,\"bytes\":%llu,\"entries\":%llu,"
 	    "\"errors\":%llu,\"seconds_mean\":%.6f,\"seconds_best\":%.6f,\"gbps_mean\":%.4f,\"crc\":\"%08x\","
 	    "\"last_pass\":{\"open_s\":%.6f,\"first_header_s\":%.6f,\"first_block_s\":%.6f,\"total_s\":%.6f},"
 	    "\"libarchive\":\"%s\"}\n",

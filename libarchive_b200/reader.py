@@ -142,8 +142,15 @@ class ZipReader:
             self.error = "Unsupported ZIP compression method (%d: %s)" % (
                 e["method"], compression_name(e["method"]))
             return ARCHIVE_FAILED, b"", off
+        if e["warn"] & capi_const.ZW_TRUNCATED:
+            # the body runs past the end of the file: no descriptor was planned for it
+            self.error = "Truncated ZIP file body"
+            return ARCHIVE_FATAL, b"", off
         if not self._decoded:
             self._decode_all()
+        if self.i not in self._res:
+            self.error = "Truncated ZIP file body"
+            return ARCHIVE_FATAL, b"", off
         d, r = self._res[self.i]
         total = int(r.out_bytes)
         if e["method"] == 0:

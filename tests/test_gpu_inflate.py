@@ -316,9 +316,9 @@ def test_two_jobs_in_flight(ctx):
         C.memmove(h_in, z, len(z))
         batches.append((z, descs, out_bytes, h_in, h_out))
     jobs = [ctx.submit(b[3], len(b[0]), b[1], b[4], b[2]) for b in batches[:2]]
-    # four jobs may be in flight on one context; a fifth is refused
+    # five jobs may be in flight on one context; a sixth is refused
     extra = [ctx.submit(batches[2][3], len(batches[2][0]), batches[2][1], batches[2][4], batches[2][2])
-             for _ in range(2)]
+             for _ in range(3)]
     with pytest.raises(capi.B2IError):
         ctx.submit(batches[2][3], len(batches[2][0]), batches[2][1], batches[2][4], batches[2][2])
     for j in extra:

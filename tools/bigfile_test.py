@@ -34,12 +34,15 @@ def run(cmd, timeout=1800):
     return p, time.time() - t, rss
 
 out = {"entries": n, "out_bytes": n * each, "file_bytes": size}
-p, dt, rss = run(["libarchive_b200/api_bench", path, "--file", "--mode", "block", "--steps", "1", "--warmup", "0"])
+p, dt, rss = run(["libarchive_b200/api_bench", path, "--file", "--mode", "block", "--steps", "1", "--warmup", "1"])   # the warm-up pass pays the CUDA context (seconds in a cold process)
 j = json.loads(p.stdout.strip().splitlines()[-1])
 out["dropin_open_filename_block"] = {"GBps": j["gbps_mean"], "seconds": j["seconds_mean"], "errors": j["errors"],
-                                     "max_rss_MiB_of_children_so_far": rss / 1024.0, "phases": j["last_pass"]}
+                                     "peak_resident_MiB": j["vm_hwm_kb"] / 1024.0,
+                                     "resident_at_exit_MiB": {"anon": j["rss_anon_kb"] / 1024.0, "file": j["rss_file_kb"] / 1024.0,
+                                                              "shmem_pinned": j["rss_shmem_kb"] / 1024.0},
+                                     "phases": j["last_pass"]}
 print(json.dumps(out["dropin_open_filename_block"]), flush=True)
-p, dt, rss2 = run(["libarchive_b200/api_bench", path, "--file", "--mode", "data", "--steps", "1", "--warmup", "0"])
+p, dt, rss2 = run(["libarchive_b200/api_bench", path, "--file", "--mode", "data", "--steps", "1", "--warmup", "1"])
 j = json.loads(p.stdout.strip().splitlines()[-1])
 out["dropin_open_filename_data64k"] = {"GBps": j["gbps_mean"], "seconds": j["seconds_mean"], "errors": j["errors"]}
 print(json.dumps(out["dropin_open_filename_data64k"]), flush=True)
