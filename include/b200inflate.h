@@ -168,6 +168,9 @@ int  b2i_submit(b2i_ctx *, const void *host_in, size_t in_bytes,
                 const b2i_stream_desc *descs, size_t n,
                 void *host_out, size_t out_bytes, b2i_job **job);
 int  b2i_wait(b2i_job *job, b2i_stream_result *res /* n entries */);
+/* blocks until the job's input has been copied to the device: host_in may then be
+ * released (a read filter consumes its upstream bytes) while the job decodes on */
+int  b2i_job_wait_input(b2i_job *job);
 
 /* The same over several GPUs of one box: the batch is partitioned on the
  * host (b2i_partition_contiguous, or b2i_partition_lpt when a few streams dominate),

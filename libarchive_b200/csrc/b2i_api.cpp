@@ -848,6 +848,18 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 	return B2I_OK;
 }
 
+/* the job's input has been copied to the device: host_in may be reused or released */
+extern "C" int b2i_job_wait_input(b2i_job *J)
+{
+	if (J == NULL || !J->busy)
+		return B2I_E_INVAL;
+	if (J->K == 0)
+		return B2I_OK;
+	b2i_ctx *c = J->ctx;
+	CU(c, cudaEventSynchronize(J->ev_in[J->K - 1]));     /* copies of one direction run in submission order */
+	return B2I_OK;
+}
+
 extern "C" int b2i_wait(b2i_job *J, b2i_stream_result *res)
 {
 	if (J == NULL || !J->busy)

@@ -14,7 +14,10 @@
  * bytes is scanned for the BGZF member chain (BSIZE in the 'BC' extra
  * subfield), every complete member of the window becomes a descriptor, ONE
  * device pass decodes them all, and read() serves the decoded bytes in blocks
- * of at most 64 KiB (gzip.c:314).  A member without BSIZE is decoded on the
+ * of at most 64 KiB (gzip.c:314).  The chain is known without decoding, so the
+ * NEXT window is submitted (b2i_submit) as soon as the current one has been
+ * collected: it is copied in, decoded and copied out into a second pinned
+ * buffer while the current one is served.  A member without BSIZE is decoded on the
  * device from "here to the end of the window"; the number of bytes it consumed
  * locates its trailer and the next header.  So that format bidding on a large
  * member does not have to decode all of it, the FIRST block of such a member is
@@ -46,7 +49,7 @@
 #include <stdio.h>
 
 #define OUT_BLOCK      (64 * 1024)            /* gzip.c:314 */
-#define WINDOW_TARGET  ((size_t)96 << 20)     /* decode at most this much input per device pass */
+#define WINDOW_TARGET  ((size_t)48 << 20)     /* decode at most this much input per device pass */
 #define WINDOW_READ    ((size_t)16 << 20)     /* what a block-sized source (a file) is asked to have
                                                  buffered before a pass: one pass per 64 KiB read
                                                  block would be one pass per three members */
@@ -64,7 +67,16 @@ struct gz_b200 {
 	uint32_t        mtime;
 	char           *name;
 	int             have_meta;
+	/* the BGZF window decoding ahead (b2i_submit): its own pinned buffer, descriptors, results */
+	b2i_job        *job;
+	unsigned char  *jbuf;         /* decoded bytes land at jbuf + OUT_BLOCK (room for the tail of `out`) */
+	size_t          jbuf_cap, jn;
+	b2i_stream_desc   *jd;
+	b2i_stream_result *jr;
 };
+
+static int	bgzf_submit(struct archive_read_filter *, const unsigned char *, const b2i_gzip_member *, size_t);
+static int	bgzf_collect(struct archive_read_filter *);
 
 static int	gz_bid(struct archive_read_filter_bidder *, struct archive_read_filter *);
 static int	gz_init(struct archive_read_filter *);
@@ -185,6 +197,144 @@ make_room(struct gz_b200 *g, size_t need)
 	return (0);
 }
 
+/* Look at what is buffered upstream; if a BGZF chain starts there, return it.  *pp: the
+ * read-ahead view.  n == 0: not a (complete) BGZF member at the read position. */
+static int
+bgzf_scan(struct archive_read_filter *up, const unsigned char **pp, b2i_gzip_member **mem, size_t *n)
+{
+	const unsigned char *p;
+	ssize_t avail;
+	size_t end = 0;
+
+	*mem = NULL;
+	*n = 0;
+	/* a memory source answers with everything it has; a file source (64 KiB read blocks,
+	 * archive_read_open_filename.c:389-461) is asked to collect a window's worth first */
+	p = __archive_read_filter_ahead(up, 18, &avail);
+	if (p != NULL && avail < (ssize_t)WINDOW_READ && p[0] == 0x1f && p[1] == 0x8b && (p[3] & 4) &&
+	    p[12] == 'B' && p[13] == 'C')
+		(void)__archive_read_filter_ahead(up, WINDOW_READ, &avail);    /* NULL: fewer bytes are left */
+	p = __archive_read_filter_ahead(up, 1, &avail);
+	*pp = p;
+	if (p == NULL || avail <= 0)
+		return (0);
+	if (b2i_gzip_scan_bgzf(p, (size_t)avail, 0, mem, n, &end) != B2I_OK)
+		return (-1);
+	return (0);
+}
+
+/* queue one device pass over the members of the chain that fit a window; their input is
+ * consumed upstream as soon as it has been copied to the device */
+static int
+bgzf_submit(struct archive_read_filter *self, const unsigned char *p, const b2i_gzip_member *mem, size_t n)
+{
+	struct gz_b200 *g = (struct gz_b200 *)self->data;
+	size_t out = 0, in_used = 0, m_used = 0, i;
+	int rc;
+
+	free(g->jd);
+	free(g->jr);
+	g->jd = calloc(n, sizeof(*g->jd));
+	g->jr = calloc(n, sizeof(*g->jr));
+	if (g->jd == NULL || g->jr == NULL)
+		return (fatal(self, g, "Can't allocate data for gzip decompression"));
+	for (i = 0; i < n; i++) {
+		b2i_stream_desc *d = &g->jd[i];
+		if (i > 0 && mem[i].header_offset >= WINDOW_TARGET)
+			break;
+		d->in_off = mem[i].deflate_offset;
+		d->in_len = mem[i].deflate_len;
+		d->expect_out = mem[i].isize;
+		d->expect_crc = mem[i].crc32;
+		d->method = B2I_METHOD_DEFLATE;
+		d->flags = g->verify ? 0 : B2I_F_NO_CRC;
+		d->out_off = out;
+		d->out_cap = mem[i].isize;
+		out = (out + mem[i].isize + 15) & ~(size_t)15;
+		in_used = (size_t)(mem[i].deflate_offset + mem[i].deflate_len + 8);
+		m_used = i + 1;
+	}
+	note_header(g, p, &mem[m_used - 1]);
+	if (g->jbuf == NULL || g->jbuf_cap < OUT_BLOCK + out + 16) {
+		b200_buf_release(g->jbuf, g->jbuf_cap);
+		g->jbuf = b200_buf_acquire(OUT_BLOCK + out + 16 + (out >> 3), &g->jbuf_cap);
+		if (g->jbuf == NULL) {
+			g->jbuf_cap = 0;
+			return (fatal(self, g, "Can't allocate data for gzip decompression"));
+		}
+	}
+	g->jn = m_used;
+	rc = b2i_submit(g->ctx, p, in_used, g->jd, m_used, g->jbuf + OUT_BLOCK, out, &g->job);
+	if (rc == B2I_OK)
+		rc = b2i_job_wait_input(g->job);
+	if (rc != B2I_OK) {
+		g->ctx_bad = (rc == B2I_E_CUDA);
+		return (fatal(self, g, b2i_last_error(g->ctx)));
+	}
+	__archive_read_filter_consume(self->upstream, (int64_t)in_used);
+	return (ARCHIVE_OK);
+}
+
+/* wait for the window in flight, make its buffer the one being served (the few bytes still
+ * pending move in front of it) and start the window after it */
+static int
+bgzf_collect(struct archive_read_filter *self)
+{
+	struct gz_b200 *g = (struct gz_b200 *)self->data;
+	unsigned char *dst = g->jbuf + OUT_BLOCK, *t;
+	size_t pending = g->out_len - g->served, w = 0, i, tc;
+	int rc;
+
+	rc = b2i_wait(g->job, g->jr);
+	g->job = NULL;
+	if (rc != B2I_OK) {
+		g->ctx_bad = (rc == B2I_E_CUDA);
+		return (fatal(self, g, b2i_last_error(g->ctx)));
+	}
+	/* members are served back to back: close the 16-byte alignment gaps */
+	for (i = 0; i < g->jn; i++) {
+		const b2i_stream_desc *d = &g->jd[i];
+		const b2i_stream_result *r = &g->jr[i];
+		int bad = r->status != B2I_S_OK || (r->flags & B2I_R_IN_MISMATCH) ||
+		    (g->verify && (r->flags & (B2I_R_CRC_MISMATCH | B2I_R_OUT_MISMATCH)));
+		if (w != d->out_off)
+			memmove(dst + w, dst + d->out_off, (size_t)r->out_bytes);
+		w += (size_t)r->out_bytes;
+		if (bad) {
+			/* the reference has already handed out the full blocks before the bad
+			 * spot when zlib reports it; the partial block is dropped */
+			g->pending_fail = "gzip decompression failed";
+			break;
+		}
+	}
+	/* next_window is only called with less than one block pending */
+	if (pending > OUT_BLOCK)
+		return (fatal(self, g, "internal error: gzip window"));
+	if (pending)
+		memcpy(dst - pending, g->out + g->served, pending);
+	t = g->out; g->out = g->jbuf; g->jbuf = t;
+	tc = g->out_cap; g->out_cap = g->jbuf_cap; g->jbuf_cap = tc;
+	g->served = OUT_BLOCK - pending;
+	g->out_len = OUT_BLOCK + w;
+	if (g->pending_fail == NULL) {
+		/* the chain goes on: decode the next window while this one is served */
+		const unsigned char *p;
+		b2i_gzip_member *mem;
+		size_t n;
+		if (bgzf_scan(self->upstream, &p, &mem, &n) != 0)
+			return (fatal(self, g, "Out of memory"));
+		if (n > 0) {
+			rc = bgzf_submit(self, p, mem, n);
+			b2i_free(mem);
+			if (rc != ARCHIVE_OK)
+				return (rc);
+		} else {
+			b2i_free(mem);
+		}
+	}
+	return (ARCHIVE_OK);
+}
+
 /* decode the next window of members and append the bytes to g->out */
 static int
 next_window(struct archive_read_filter *self)
@@ -194,7 +344,10 @@ next_window(struct archive_read_filter *self)
 	const unsigned char *p;
 	ssize_t avail;
 	b2i_gzip_member *mem = NULL;
-	size_t n = 0, end = 0, i;
+	size_t n = 0, end = 0;
+
+	if (g->job != NULL)
+		return (bgzf_collect(self));       /* the window that was decoding while we served */
 
 	/* a memory source answers with everything it has; a file source (64 KiB read blocks,
 	 * archive_read_open_filename.c:389-461) is asked to collect a window's worth first */
@@ -245,63 +398,11 @@ next_window(struct archive_read_filter *self)
 		}
 	}
 	if (n > 0) {
-		b2i_stream_desc *d = calloc(n, sizeof(*d));
-		b2i_stream_result *r = calloc(n, sizeof(*r));
-		size_t out = 0, in_used = 0, m_used = 0;
-		int rc;
-
-		if (d == NULL || r == NULL) {
-			free(d); free(r); b2i_free(mem);
-			return (fatal(self, g, "Can't allocate data for gzip decompression"));
-		}
-		for (i = 0; i < n; i++) {
-			if (i > 0 && mem[i].header_offset >= WINDOW_TARGET)
-				break;
-			d[i].in_off = mem[i].deflate_offset;
-			d[i].in_len = mem[i].deflate_len;
-			d[i].expect_out = mem[i].isize;
-			d[i].expect_crc = mem[i].crc32;
-			d[i].method = B2I_METHOD_DEFLATE;
-			d[i].flags = g->verify ? 0 : B2I_F_NO_CRC;
-			d[i].out_off = out;
-			d[i].out_cap = mem[i].isize;
-			out = (out + mem[i].isize + 15) & ~(size_t)15;
-			in_used = (size_t)(mem[i].deflate_offset + mem[i].deflate_len + 8);
-			m_used = i + 1;
-		}
-		note_header(g, p, &mem[m_used - 1]);
-		if (make_room(g, out) != 0) {
-			free(d); free(r); b2i_free(mem);
-			return (fatal(self, g, "Can't allocate data for gzip decompression"));
-		}
-		unsigned char *dst = g->out + g->out_len;
-		rc = b2i_decode_host(g->ctx, p, in_used, d, m_used, dst, out, r);
-		if (rc != B2I_OK) {
-			free(d); free(r); b2i_free(mem);
-			{ g->ctx_bad = (rc == B2I_E_CUDA); return (fatal(self, g, b2i_last_error(g->ctx))); }
-		}
-		/* members are served back to back: close the 16-byte alignment gaps */
-		size_t w = 0;
-		for (i = 0; i < m_used; i++) {
-			int bad = r[i].status != B2I_S_OK || (r[i].flags & B2I_R_IN_MISMATCH) ||
-			    (g->verify && (r[i].flags & (B2I_R_CRC_MISMATCH | B2I_R_OUT_MISMATCH)));
-			if (bad) {
-				/* the reference has already handed out the full blocks before the bad
-				 * spot when zlib reports it; the partial block is dropped */
-				if (w != d[i].out_off)
-					memmove(dst + w, dst + d[i].out_off, (size_t)r[i].out_bytes);
-				w += (size_t)r[i].out_bytes;
-				g->pending_fail = "gzip decompression failed";
-				break;
-			}
-			if (w != d[i].out_off)
-				memmove(dst + w, dst + d[i].out_off, (size_t)r[i].out_bytes);
-			w += (size_t)r[i].out_bytes;
-		}
-		g->out_len += w;
-		__archive_read_filter_consume(up, (int64_t)in_used);
-		free(d); free(r); b2i_free(mem);
-		return (ARCHIVE_OK);
+		int r = bgzf_submit(self, p, mem, n);
+		b2i_free(mem);
+		if (r != ARCHIVE_OK)
+			return (r);
+		return (bgzf_collect(self));
 	}
 	b2i_free(mem);
 
@@ -447,6 +548,11 @@ gz_close(struct archive_read_filter *self)
 {
 	struct gz_b200 *g = (struct gz_b200 *)self->data;
 
+	if (g->job != NULL)
+		(void)b2i_wait(g->job, g->jr);      /* nothing may still be writing into jbuf */
+	b200_buf_release(g->jbuf, g->jbuf_cap);
+	free(g->jd);
+	free(g->jr);
 	b200_buf_release(g->out, g->out_cap);
 	b200_ctx_release(g->ctx, !g->ctx_bad);
 	free(g->name);

@@ -63,6 +63,7 @@ struct b2i_job {
 	const void *in; size_t in_bytes;
 	b2i_stream_desc *descs; size_t n;
 	void *out; size_t out_bytes;
+	void *owned;
 };
 
 int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes, const b2i_stream_desc *descs, size_t n,
@@ -78,10 +79,24 @@ int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes, const b2i_strea
 	return B2I_OK;
 }
 
+/* the shim decodes at wait time, from the caller's memory: keep a copy of the input */
+int b2i_job_wait_input(b2i_job *j)
+{
+	if (j->n && j->owned == NULL) {
+		j->owned = malloc(j->in_bytes ? j->in_bytes : 1);
+		if (j->owned == NULL)
+			return B2I_E_NOMEM;
+		memcpy(j->owned, j->in, j->in_bytes);
+		j->in = j->owned;
+	}
+	return B2I_OK;
+}
+
 int b2i_wait(b2i_job *j, b2i_stream_result *res)
 {
 	int rc = j->n ? b2i_decode_host(j->c, j->in, j->in_bytes, j->descs, j->n, j->out, j->out_bytes, res) : B2I_OK;
 	free(j->descs);
+	free(j->owned);
 	free(j);
 	return rc;
 }
