@@ -201,7 +201,8 @@ typedef struct b2i_pipe_opts {
 	                                   (callback sources: at most 64 MiB) */
 	size_t first_window_out_bytes;  /* 0: a quarter of that (first bytes arrive sooner) */
 	int    windows_per_device;      /* ring depth, 0: 5 (four of them in flight) */
-	int    copy_threads;            /* staging threads for pageable memory, 0: 6 */
+	int    copy_threads;            /* reserved (the staging threads are one process-wide pool of 6,
+	                                   B2I_COPY_THREADS) */
 } b2i_pipe_opts;
 int  b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, uint64_t mem_size,
                    b2i_fill_fn fill, void *user, const b2i_stream_desc *descs, size_t n,

@@ -41,6 +41,7 @@ struct b2i_job {
 	bool busy, ev_ready;
 	uint8_t *d_in;  size_t d_in_cap;
 	uint8_t *d_out; size_t d_out_cap;
+	uint8_t *h_stage; size_t h_stage_cap;   /* pinned staging for pageable input */
 	uint8_t *arena_d; uint8_t *arena_h; size_t arena_cap;
 	cudaEvent_t ev_in[B2I_PIPE_SLICES], ev_k[B2I_PIPE_SLICES], ev_done;
 	b2i_plan *plans[B2I_PIPE_SLICES];
@@ -197,6 +198,7 @@ extern "C" void b2i_ctx_destroy(b2i_ctx *c)
 				b2i_plan_destroy(J->plans[k]);
 		cudaFree(J->d_in);
 		cudaFree(J->d_out);
+		cudaFreeHost(J->h_stage);
 		cudaFree(J->arena_d);
 		cudaFreeHost(J->arena_h);
 		if (J->ev_ready) {
@@ -275,6 +277,7 @@ extern "C" int b2i_memcpy_d2h(b2i_ctx *c, void *dst, const void *src, size_t byt
 /* ---- plan ------------------------------------------------------------------ */
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+void b2i_parallel_copy(void *dst, const void *src, size_t len);      /* b2i_pipe.cpp */
 
 static size_t plan_block_bound(size_t n, size_t stored_bytes)
 {
@@ -744,6 +747,29 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 			if (descs[i].method == B2I_METHOD_STORED && !(descs[i].flags & B2I_F_NO_COPY))
 				mirror = NULL;
 	}
+	/* pageable input of some size is staged through the job's own pinned buffer */
+	uint8_t *stage = NULL;
+	if (in_bytes >= ((size_t)4 << 20) && in_bytes <= ((size_t)1 << 30) && getenv("B2I_NO_STAGE") == NULL) {
+		cudaPointerAttributes pa;
+		bool pageable = true;
+		if (cudaPointerGetAttributes(&pa, host_in) == cudaSuccess)
+			pageable = pa.type == cudaMemoryTypeUnregistered;
+		else
+			cudaGetLastError();
+		if (pageable) {
+			if (J->h_stage_cap < in_bytes + 64) {
+				cudaFreeHost(J->h_stage);
+				J->h_stage = NULL;
+				J->h_stage_cap = 0;
+				size_t want = in_bytes + in_bytes / 4 + 64;
+				if (cudaHostAlloc((void **)&J->h_stage, want, cudaHostAllocDefault) == cudaSuccess)
+					J->h_stage_cap = want;
+				else
+					cudaGetLastError();
+			}
+			stage = J->h_stage;          /* NULL: no pinned memory to be had, the driver copies */
+		}
+	}
 	b2i_plan **plans = J->plans;
 	rc = B2I_OK;
 	for (size_t s = 0; s < K && rc == B2I_OK; s++) {
@@ -768,7 +794,15 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 			auto flush_in = [&]() {
 				if (lo < hi) {
 					lo &= ~(uint64_t)15;
-					cudaError_t e = cudaMemcpyAsync(J->d_in + lo, (const uint8_t *)host_in + lo, hi - lo,
+					const uint8_t *src = (const uint8_t *)host_in + lo;
+					if (stage != NULL) {
+						/* pageable input: several threads copy the run into pinned staging and
+						 * the DMA runs from there (the driver's own pageable path is a single
+						 * blocking copy at about 10 GB/s) */
+						b2i_parallel_copy(stage + lo, src, hi - lo);
+						src = stage + lo;
+					}
+					cudaError_t e = cudaMemcpyAsync(J->d_in + lo, src, hi - lo,
 					    cudaMemcpyHostToDevice, c->s_in);
 					if (e != cudaSuccess) { rc = fail(c, B2I_E_CUDA, "H2D: %s", cudaGetErrorString(e)); bad = true; }
 				}

@@ -167,6 +167,21 @@ struct CopyPool {
 	}
 };
 
+/* one pool for the whole process, started on first use */
+CopyPool *shared_copiers()
+{
+	static std::mutex mu;
+	static CopyPool *pool = NULL;
+	std::lock_guard<std::mutex> g(mu);
+	if (pool == NULL) {
+		int n = 6;
+		if (const char *ev = getenv("B2I_COPY_THREADS"))
+			n = std::max(0, atoi(ev));
+		pool = new CopyPool(n);
+	}
+	return pool;
+}
+
 enum SlotState { EMPTY = 0, FILLING, FILLED, INFLIGHT, READY };
 
 struct Window {
@@ -186,6 +201,13 @@ struct Slot {
 };
 
 } // namespace
+
+/* pageable -> pinned with several threads (the driver's own pageable path runs at about
+ * 10 GB/s and blocks the caller): used by the pipeline and by b2i_submit's staging */
+void b2i_parallel_copy(void *dst, const void *src, size_t len)
+{
+	shared_copiers()->copy(dst, src, len);
+}
 
 struct b2i_pipe {
 	std::vector<b2i_ctx *> ctxs;
@@ -382,7 +404,6 @@ extern "C" int b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, ui
 	}
 	size_t first_out = opts && opts->first_window_out_bytes ? opts->first_window_out_bytes : window_out / 4;
 	int depth = opts && opts->windows_per_device > 0 ? opts->windows_per_device : 5;
-	int copy_threads = opts && opts->copy_threads > 0 ? opts->copy_threads : 6;
 	if (const char *ev = getenv("B2I_PIPE_WINDOW_MB"))
 		window_out = (size_t)std::max(1, atoi(ev)) << 20, first_out = window_out / 4;
 	if (const char *ev = getenv("B2I_PIPE_FIRST_MB"))
@@ -410,7 +431,7 @@ extern "C" int b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, ui
 		else
 			cudaGetLastError();
 		if (!p->mem_pinned)
-			p->copiers = new CopyPool(copy_threads);
+			p->copiers = shared_copiers();
 	}
 
 	/* windows: consecutive streams while the output (and the input span) stays bounded */
@@ -423,7 +444,6 @@ extern "C" int b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, ui
 		uint64_t lo = cur.in_lo, hi = cur.in_hi;
 		if (data) {
 			if (mem != NULL && d.in_off + d.in_len > mem_size) {
-				delete p->copiers;
 				delete p;
 				return B2I_E_INVAL;
 			}
@@ -574,7 +594,6 @@ extern "C" void b2i_pipe_close(b2i_pipe *p)
 	p->cv_work.notify_all();
 	for (auto &t : p->workers)
 		t.join();
-	delete p->copiers;
 	for (Slot &s : p->slots) {
 		g_pinned.put(s.h_in, s.h_in_cap);
 		g_pinned.put(s.h_out, s.h_out_cap);

@@ -49,7 +49,8 @@
 #include <stdio.h>
 
 #define OUT_BLOCK      (64 * 1024)            /* gzip.c:314 */
-#define WINDOW_TARGET  ((size_t)48 << 20)     /* decode at most this much input per device pass */
+#define WINDOW_TARGET  ((size_t)32 << 20)     /* decode at most this much input per device pass */
+#define GZ_JOBS        3                      /* BGZF windows in flight ahead of the one being served */
 #define WINDOW_READ    ((size_t)16 << 20)     /* what a block-sized source (a file) is asked to have
                                                  buffered before a pass: one pass per 64 KiB read
                                                  block would be one pass per three members */
@@ -67,12 +68,17 @@ struct gz_b200 {
 	uint32_t        mtime;
 	char           *name;
 	int             have_meta;
-	/* the BGZF window decoding ahead (b2i_submit): its own pinned buffer, descriptors, results */
-	b2i_job        *job;
-	unsigned char  *jbuf;         /* decoded bytes land at jbuf + OUT_BLOCK (room for the tail of `out`) */
-	size_t          jbuf_cap, jn;
-	b2i_stream_desc   *jd;
-	b2i_stream_result *jr;
+	/* BGZF windows decoding ahead (b2i_submit), oldest first: each with its own pinned buffer
+	 * (decoded bytes land at buf + OUT_BLOCK: room for the tail of `out`), descriptors, results */
+	struct gz_job {
+		b2i_job        *job;
+		unsigned char  *buf;
+		size_t          cap, n;
+		b2i_stream_desc   *d;
+		b2i_stream_result *r;
+	} q[GZ_JOBS];
+	int             qh, qn;       /* head and length of the queue (slots are used round-robin) */
+	size_t          windows;      /* BGZF windows submitted so far */
 };
 
 static int	bgzf_submit(struct archive_read_filter *, const unsigned char *, const b2i_gzip_member *, size_t);
@@ -229,18 +235,20 @@ static int
 bgzf_submit(struct archive_read_filter *self, const unsigned char *p, const b2i_gzip_member *mem, size_t n)
 {
 	struct gz_b200 *g = (struct gz_b200 *)self->data;
+	struct gz_job *j = &g->q[(g->qh + g->qn) % GZ_JOBS];
 	size_t out = 0, in_used = 0, m_used = 0, i;
 	int rc;
 
-	free(g->jd);
-	free(g->jr);
-	g->jd = calloc(n, sizeof(*g->jd));
-	g->jr = calloc(n, sizeof(*g->jr));
-	if (g->jd == NULL || g->jr == NULL)
+	free(j->d);
+	free(j->r);
+	j->d = calloc(n, sizeof(*j->d));
+	j->r = calloc(n, sizeof(*j->r));
+	if (j->d == NULL || j->r == NULL)
 		return (fatal(self, g, "Can't allocate data for gzip decompression"));
 	for (i = 0; i < n; i++) {
-		b2i_stream_desc *d = &g->jd[i];
-		if (i > 0 && mem[i].header_offset >= WINDOW_TARGET)
+		b2i_stream_desc *d = &j->d[i];
+		/* the first window is small: the caller (format bidding, the first read) waits for it */
+		if (i > 0 && mem[i].header_offset >= (g->windows ? WINDOW_TARGET : WINDOW_TARGET / 4))
 			break;
 		d->in_off = mem[i].deflate_offset;
 		d->in_len = mem[i].deflate_len;
@@ -255,46 +263,76 @@ bgzf_submit(struct archive_read_filter *self, const unsigned char *p, const b2i_
 		m_used = i + 1;
 	}
 	note_header(g, p, &mem[m_used - 1]);
-	if (g->jbuf == NULL || g->jbuf_cap < OUT_BLOCK + out + 16) {
-		b200_buf_release(g->jbuf, g->jbuf_cap);
-		g->jbuf = b200_buf_acquire(OUT_BLOCK + out + 16 + (out >> 3), &g->jbuf_cap);
-		if (g->jbuf == NULL) {
-			g->jbuf_cap = 0;
+	if (j->buf == NULL || j->cap < OUT_BLOCK + out + 16) {
+		b200_buf_release(j->buf, j->cap);
+		j->buf = b200_buf_acquire(OUT_BLOCK + out + 16 + (out >> 3), &j->cap);
+		if (j->buf == NULL) {
+			j->cap = 0;
 			return (fatal(self, g, "Can't allocate data for gzip decompression"));
 		}
 	}
-	g->jn = m_used;
-	rc = b2i_submit(g->ctx, p, in_used, g->jd, m_used, g->jbuf + OUT_BLOCK, out, &g->job);
+	j->n = m_used;
+	rc = b2i_submit(g->ctx, p, in_used, j->d, m_used, j->buf + OUT_BLOCK, out, &j->job);
 	if (rc == B2I_OK)
-		rc = b2i_job_wait_input(g->job);
+		rc = b2i_job_wait_input(j->job);
 	if (rc != B2I_OK) {
 		g->ctx_bad = (rc == B2I_E_CUDA);
 		return (fatal(self, g, b2i_last_error(g->ctx)));
 	}
+	g->qn++;
+	g->windows++;
 	__archive_read_filter_consume(self->upstream, (int64_t)in_used);
 	return (ARCHIVE_OK);
 }
 
-/* wait for the window in flight, make its buffer the one being served (the few bytes still
- * pending move in front of it) and start the window after it */
+/* keep GZ_JOBS windows decoding ahead as long as the chain goes on */
+static int
+bgzf_top_up(struct archive_read_filter *self)
+{
+	struct gz_b200 *g = (struct gz_b200 *)self->data;
+
+	while (g->qn < GZ_JOBS && g->pending_fail == NULL) {
+		const unsigned char *p;
+		b2i_gzip_member *mem;
+		size_t n;
+		int rc;
+		if (bgzf_scan(self->upstream, &p, &mem, &n) != 0)
+			return (fatal(self, g, "Out of memory"));
+		if (n == 0) {
+			b2i_free(mem);
+			break;
+		}
+		rc = bgzf_submit(self, p, mem, n);
+		b2i_free(mem);
+		if (rc != ARCHIVE_OK)
+			return (rc);
+	}
+	return (ARCHIVE_OK);
+}
+
+/* wait for the oldest window in flight, make its buffer the one being served (the few bytes
+ * still pending move in front of it) and queue the windows after it */
 static int
 bgzf_collect(struct archive_read_filter *self)
 {
 	struct gz_b200 *g = (struct gz_b200 *)self->data;
-	unsigned char *dst = g->jbuf + OUT_BLOCK, *t;
+	struct gz_job *j = &g->q[g->qh];
+	unsigned char *dst = j->buf + OUT_BLOCK, *t;
 	size_t pending = g->out_len - g->served, w = 0, i, tc;
 	int rc;
 
-	rc = b2i_wait(g->job, g->jr);
-	g->job = NULL;
+	rc = b2i_wait(j->job, j->r);
+	j->job = NULL;
+	g->qh = (g->qh + 1) % GZ_JOBS;
+	g->qn--;
 	if (rc != B2I_OK) {
 		g->ctx_bad = (rc == B2I_E_CUDA);
 		return (fatal(self, g, b2i_last_error(g->ctx)));
 	}
 	/* members are served back to back: close the 16-byte alignment gaps */
-	for (i = 0; i < g->jn; i++) {
-		const b2i_stream_desc *d = &g->jd[i];
-		const b2i_stream_result *r = &g->jr[i];
+	for (i = 0; i < j->n; i++) {
+		const b2i_stream_desc *d = &j->d[i];
+		const b2i_stream_result *r = &j->r[i];
 		int bad = r->status != B2I_S_OK || (r->flags & B2I_R_IN_MISMATCH) ||
 		    (g->verify && (r->flags & (B2I_R_CRC_MISMATCH | B2I_R_OUT_MISMATCH)));
 		if (w != d->out_off)
@@ -312,27 +350,22 @@ bgzf_collect(struct archive_read_filter *self)
 		return (fatal(self, g, "internal error: gzip window"));
 	if (pending)
 		memcpy(dst - pending, g->out + g->served, pending);
-	t = g->out; g->out = g->jbuf; g->jbuf = t;
-	tc = g->out_cap; g->out_cap = g->jbuf_cap; g->jbuf_cap = tc;
+	t = g->out; g->out = j->buf; j->buf = t;
+	tc = g->out_cap; g->out_cap = j->cap; j->cap = tc;
 	g->served = OUT_BLOCK - pending;
 	g->out_len = OUT_BLOCK + w;
-	if (g->pending_fail == NULL) {
-		/* the chain goes on: decode the next window while this one is served */
-		const unsigned char *p;
-		b2i_gzip_member *mem;
-		size_t n;
-		if (bgzf_scan(self->upstream, &p, &mem, &n) != 0)
-			return (fatal(self, g, "Out of memory"));
-		if (n > 0) {
-			rc = bgzf_submit(self, p, mem, n);
-			b2i_free(mem);
-			if (rc != ARCHIVE_OK)
-				return (rc);
-		} else {
-			b2i_free(mem);
+	if (g->pending_fail != NULL) {
+		/* what was decoding behind a bad member is dropped */
+		while (g->qn > 0) {
+			struct gz_job *k = &g->q[g->qh];
+			(void)b2i_wait(k->job, k->r);
+			k->job = NULL;
+			g->qh = (g->qh + 1) % GZ_JOBS;
+			g->qn--;
 		}
+		return (ARCHIVE_OK);
 	}
-	return (ARCHIVE_OK);
+	return (bgzf_top_up(self));
 }
 
 /* decode the next window of members and append the bytes to g->out */
@@ -346,8 +379,8 @@ next_window(struct archive_read_filter *self)
 	b2i_gzip_member *mem = NULL;
 	size_t n = 0, end = 0;
 
-	if (g->job != NULL)
-		return (bgzf_collect(self));       /* the window that was decoding while we served */
+	if (g->qn > 0)
+		return (bgzf_collect(self));       /* the oldest of the windows that were decoding while we served */
 
 	/* a memory source answers with everything it has; a file source (64 KiB read blocks,
 	 * archive_read_open_filename.c:389-461) is asked to collect a window's worth first */
@@ -548,11 +581,17 @@ gz_close(struct archive_read_filter *self)
 {
 	struct gz_b200 *g = (struct gz_b200 *)self->data;
 
-	if (g->job != NULL)
-		(void)b2i_wait(g->job, g->jr);      /* nothing may still be writing into jbuf */
-	b200_buf_release(g->jbuf, g->jbuf_cap);
-	free(g->jd);
-	free(g->jr);
+	while (g->qn > 0) {                     /* nothing may still be writing into the buffers */
+		struct gz_job *k = &g->q[g->qh];
+		(void)b2i_wait(k->job, k->r);
+		g->qh = (g->qh + 1) % GZ_JOBS;
+		g->qn--;
+	}
+	for (int i = 0; i < GZ_JOBS; i++) {
+		b200_buf_release(g->q[i].buf, g->q[i].cap);
+		free(g->q[i].d);
+		free(g->q[i].r);
+	}
 	b200_buf_release(g->out, g->out_cap);
 	b200_ctx_release(g->ctx, !g->ctx_bad);
 	free(g->name);

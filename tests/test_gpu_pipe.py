@@ -84,6 +84,20 @@ def test_pipe_oversized_stream_and_pinned_source(ctx):
     L.b2i_host_free(h)
 
 
+def test_pipe_two_contexts_round_robin(ctx):
+    """Windows of one archive go round-robin over the contexts (one per GPU when the box has
+    several; two contexts on one device otherwise): same bytes, in order."""
+    L = capi.lib()
+    ctx2 = capi.Context(1 if L.b2i_device_count() > 1 else 0)
+    z, members, descs = _archive(n=260, seed=13, stored_every=9)
+    buf = C.create_string_buffer(z, len(z) + 64)
+    p = capi.Pipe([ctx, ctx2], descs, mem=buf, mem_size=len(z), window_out=1 << 20, first_window_out=1 << 19)
+    assert p.windows > 6
+    _check_all(p, members, descs)
+    p.close()
+    ctx2.close()
+
+
 def test_decode_host_multi_two_contexts(ctx):
     """Two contexts (here on the same device) share one batch: contiguous partition for a
     uniform batch, LPT when one stream dominates; results and bytes equal zlib's."""
