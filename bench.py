@@ -533,12 +533,23 @@ def strong_scaling(rig, name, scale, rank, K, W):
     else:
         # rank 0 builds the archive once; the others read it from shared memory
         path = "/dev/shm/b2i_strong_%s_%d.bin" % (name, os.getppid())
+        alt = "/tmp/b2i_strong_%s_%d.bin" % (name, os.getppid())
         if rank == 0:
             archive, kind = build_workload(name, 0, scale)
-            with open(path + ".tmp", "wb") as f:
-                f.write(archive)
-            os.rename(path + ".tmp", path)
+            try:
+                with open(path + ".tmp", "wb") as f:
+                    f.write(archive)
+                os.rename(path + ".tmp", path)
+            except OSError:                      # a small /dev/shm: the file system will do
+                for pth in (path + ".tmp", path):
+                    if os.path.exists(pth):
+                        os.unlink(pth)
+                with open(alt + ".tmp", "wb") as f:
+                    f.write(archive)
+                os.rename(alt + ".tmp", alt)
         rig.barrier()
+        if not os.path.exists(path):
+            path = alt
         if rank != 0:
             with open(path, "rb") as f:
                 archive = f.read()
