@@ -82,15 +82,21 @@ struct PinnedPool {
 	{
 		if (p == NULL)
 			return;
+		std::vector<Buf> drop;
 		{
+			/* the newest buffers stay (the next archive most likely wants the same sizes);
+			 * the oldest ones go when the cache is over its limit */
 			std::lock_guard<std::mutex> g(mu);
-			if (cached + cap <= kMaxCached) {
-				free_.push_back({p, cap});
-				cached += cap;
-				return;
+			free_.push_back({p, cap});
+			cached += cap;
+			while (cached > kMaxCached && !free_.empty()) {
+				drop.push_back(free_.front());
+				cached -= free_.front().cap;
+				free_.erase(free_.begin());
 			}
 		}
-		cudaFreeHost(p);
+		for (const Buf &b : drop)
+			cudaFreeHost(b.p);
 	}
 };
 PinnedPool g_pinned;
