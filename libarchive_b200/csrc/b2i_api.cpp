@@ -357,6 +357,12 @@ static int b2i_plan_build(b2i_ctx *c, const b2i_stream_desc *descs, size_t n, cu
 		team_min = strtoull(ev, NULL, 10);
 	std::vector<uint32_t> big;
 	if (team_min != 0) {
+		/* a batch with fewer streams than two per SM cannot fill the GPU with single warps
+		 * anyway: its medium streams (>= 48 KiB) take a CTA each too, which cuts their
+		 * latency from ~1.5 ms to ~0.3 ms (the first window of a pipelined archive, small
+		 * archives) */
+		if (deflate.size() <= 2u * (size_t)c->num_sms && getenv("B2I_TEAM_MIN_BYTES") == NULL)
+			team_min = 48u << 10;
 		std::vector<uint32_t> small;
 		for (uint32_t i : deflate)
 			(descs[i].in_len + descs[i].out_cap >= team_min ? big : small).push_back(i);

@@ -51,7 +51,9 @@
 #endif
 #define TEAM_LANES    (32 * TEAM_WARPS)
 #define TEAM_SEG_MAX  1024u                 /* bits per lane and round, at most */
-#define TEAM_MIN_BITS ((uint64_t)TEAM_LANES * LP_SEG_MIN)
+/* below this the block is finished by warp 0 alone; a round may well be shorter than
+ * TEAM_LANES segments (lanes that start past the end of the input drop out at once) */
+#define TEAM_MIN_BITS ((uint64_t)32 * LP_SEG_MIN)
 #ifndef TEAM_CHUNK
 #define TEAM_CHUNK    (3584u * TEAM_WARPS)  /* 16-bit symbols in the chunk buffer (112 KB for 16 warps) */
 #endif
