@@ -58,6 +58,9 @@
 #define TEAM_CHUNK    (3584u * TEAM_WARPS)  /* 16-bit symbols in the chunk buffer (112 KB for 16 warps) */
 #endif
 #define TEAM_HIST     32768u                /* history ring: the deflate window */
+#ifndef TEAM_MARGIN_X2
+#define TEAM_MARGIN_X2 2u                  /* pass A starts this many half-segments early */
+#endif
 #define TEAM_SEG_INIT 288u                  /* first round: assume 3:1 */
 
 #define TC_PASS_A    1u
@@ -197,7 +200,7 @@ B2I_DEV void team_do_pass(TeamShared *ts, unsigned w, const WarpSmem *tables)
 		/* pass A only looks for the place where this lane's decoder crosses into the next
 		 * segment: starting one margin EARLIER gives it that much more input to fall into
 		 * step with the true symbol sequence before it gets there */
-		const uint32_t margin = ts->seg;
+		const uint32_t margin = ts->seg * TEAM_MARGIN_X2 / 2u;
 		start = start - ts->p0 > margin ? start - margin : ts->p0;
 	}
 	if (ts->stage_words)

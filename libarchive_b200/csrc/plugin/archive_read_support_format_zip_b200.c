@@ -234,7 +234,7 @@ gpus_for(uint64_t total_out)
 		have = ZB_MAX_GPUS;
 	if (ev != NULL && atoi(ev) >= 1)
 		return (atoi(ev) < have ? atoi(ev) : have);
-	want = (int)(total_out / ((uint64_t)512 << 20));
+	want = (int)(total_out / ((uint64_t)2 << 30));      /* one more GPU per 2 GiB of output */
 	if (want < 1)
 		want = 1;
 	return (want < have ? want : have);
