@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -127,10 +129,38 @@ extern "C" int b2i_device_count(void)
 	return n;
 }
 
+/* B2I_CALL_STATS=1: wall time and count of the entry points a plugin calls per archive,
+ * printed at exit (diagnostic for the small-archive path) */
+struct CallStat { const char *name; std::atomic<uint64_t> ns{0}, calls{0}; };
+static CallStat g_cs_ctx{"b2i_ctx_create"}, g_cs_decode{"b2i_decode_host"}, g_cs_halloc{"b2i_host_alloc"},
+    g_cs_hfree{"b2i_host_free"}, g_cs_submit{"b2i_submit"}, g_cs_wait{"b2i_wait"};
+static bool call_stats_on()
+{
+	static int on = -1;
+	if (on < 0) {
+		on = getenv("B2I_CALL_STATS") != NULL;
+		if (on)
+			atexit([] {
+				for (CallStat *c : {&g_cs_ctx, &g_cs_decode, &g_cs_submit, &g_cs_wait, &g_cs_halloc, &g_cs_hfree})
+					if (c->calls)
+						fprintf(stderr, "B2I_CALL %-16s calls %8llu  total %9.3f ms  mean %8.1f us\n", c->name,
+						    (unsigned long long)c->calls.load(), c->ns.load() / 1e6,
+						    c->ns.load() / 1e3 / (double)c->calls.load());
+			});
+	}
+	return on != 0;
+}
+struct CallTimer {
+	CallStat *s; std::chrono::steady_clock::time_point t0;
+	explicit CallTimer(CallStat &st) : s(call_stats_on() ? &st : nullptr) { if (s) t0 = std::chrono::steady_clock::now(); }
+	~CallTimer() { if (s) { s->ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); s->calls++; } }
+};
+
 extern "C" int b2i_ctx_create(int device, void *cuda_stream, b2i_ctx **out)
 {
 	if (out == NULL)
 		return B2I_E_INVAL;
+	CallTimer ct_(g_cs_ctx);
 	*out = NULL;
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
@@ -241,11 +271,18 @@ extern "C" int b2i_ctx_sync(b2i_ctx *c)
 extern "C" void *b2i_host_alloc(size_t bytes)
 {
 	void *p = NULL;
+	CallTimer ct_(g_cs_halloc);
 	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
 		return NULL;
 	return p;
 }
-extern "C" void b2i_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void b2i_host_free(void *p)
+{
+	if (p) {
+		CallTimer ct_(g_cs_hfree);
+		cudaFreeHost(p);
+	}
+}
 
 extern "C" void *b2i_device_alloc(b2i_ctx *c, size_t bytes)
 {
@@ -648,6 +685,7 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 	*job = NULL;
 	if (n != 0 && (host_in == NULL || descs == NULL))
 		return fail(c, B2I_E_INVAL, "b2i_submit: NULL argument");
+	CallTimer ct_(g_cs_submit);
 	b2i_job *J = NULL;
 	for (int i = 0; i < B2I_MAX_JOBS && J == NULL; i++)
 		if (!c->jobs[i].busy)
@@ -904,6 +942,7 @@ extern "C" int b2i_wait(b2i_job *J, b2i_stream_result *res)
 {
 	if (J == NULL || !J->busy)
 		return B2I_E_INVAL;
+	CallTimer ct_(g_cs_wait);
 	b2i_ctx *c = J->ctx;
 	int rc = B2I_OK;
 	cudaError_t e = cudaEventSynchronize(J->ev_done);
@@ -934,6 +973,7 @@ extern "C" int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		return B2I_OK;
 	if (host_in == NULL || descs == NULL || res == NULL)
 		return fail(c, B2I_E_INVAL, "b2i_decode_host: NULL argument");
+	CallTimer ct_(g_cs_decode);
 	b2i_job *J = NULL;
 	int rc = b2i_submit(c, host_in, in_bytes, descs, n, host_out, out_bytes, &J);
 	if (rc != B2I_OK)

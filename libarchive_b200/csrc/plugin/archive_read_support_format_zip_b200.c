@@ -250,11 +250,15 @@ retry_with_room(struct zip_b200 *z, b2i_ctx *ctx, const void *in, size_t in_byte
 	unsigned char *buf = NULL;
 
 	(void)z;
-	while (res->status == B2I_S_OUT_OVERFLOW && cap < ((size_t)1 << 31)) {
+	const size_t most = (size_t)d0->in_len * 1032u + 65536u;   /* deflate's expansion limit */
+
+	while (res->status == B2I_S_OUT_OVERFLOW && cap < most) {
 		b2i_stream_desc d = *d0;
 		cap = cap < 4096 ? 16384 : cap * 4;
-		b2i_host_free(buf);
-		if ((buf = b2i_host_alloc(cap + 16)) == NULL)
+		if (cap > most)
+			cap = most;
+		b200_buf_release_tagged(buf);
+		if ((buf = b200_buf_acquire_tagged(cap + 16)) == NULL)
 			break;
 		d.out_off = 0;
 		d.out_cap = cap;
@@ -374,7 +378,7 @@ entry_result(struct archive_read *a, struct zip_b200 *z, size_t ei)
 		return (&z->res[di]);
 	if (z->cur_desc == di)
 		return (&z->cur_res);
-	b2i_host_free(z->cur_retry);
+	b200_buf_release_tagged(z->cur_retry);
 	z->cur_retry = NULL;
 	if ((rc = b2i_pipe_get(z->pipe, di, &o, &in, &z->cur_res)) != B2I_OK) {
 		archive_set_error(&a->archive, ARCHIVE_ERRNO_MISC, "B200 decode failed (%d): %s", rc,
@@ -693,10 +697,10 @@ zip_b200_cleanup(struct archive_read *a)
 		b2i_pipe_close(z->pipe);            /* joins the workers before the contexts go back */
 	for (g = 1; g < z->nctx; g++)
 		b200_ctx_release(z->ctxs[g], 1);
-	b2i_host_free(z->cur_retry);
+	b200_buf_release_tagged(z->cur_retry);
 	if (z->retry != NULL)
 		for (i = 0; i < z->ndesc; i++)
-			b2i_host_free(z->retry[i]);
+			b200_buf_release_tagged(z->retry[i]);
 	free(z->retry);
 	free(z->descs);
 	free(z->res);

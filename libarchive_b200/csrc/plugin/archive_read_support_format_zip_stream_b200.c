@@ -148,6 +148,10 @@ zs_decode_entry(struct archive_read *a, struct zs_b200 *z, int64_t known, int64_
 				in_len = 0, p = "";
 		} else
 			in_len = known > 0 ? (size_t)known : (size_t)avail;
+		/* deflate cannot expand by more than 1032:1: a header that claims more gets the
+		 * honest bound, not gigabytes of pinned memory (the size check still sees expect_out) */
+		if (expect_out > 0 && (uint64_t)expect_out > (uint64_t)in_len * 1032u + 65536u)
+			cap = in_len * 1032u + 65536u;
 		if (cap < 4 * in_len && expect_out <= 0)
 			cap = 4 * in_len;
 		if (cap < 65536 && expect_out <= 0)
@@ -183,9 +187,11 @@ zs_decode_entry(struct archive_read *a, struct zs_b200 *z, int64_t known, int64_
 			}
 			/* output outgrew the announced size: decode again with room, so that the
 			 * "wrong size" message can quote the true count */
-			if (z->res.status != B2I_S_OUT_OVERFLOW || cap >= ((size_t)1 << 31))
+			if (z->res.status != B2I_S_OUT_OVERFLOW || cap >= in_len * 1032u + 65536u)
 				break;
 			cap = cap < 4096 ? 16384 : cap * 4;
+			if (cap > in_len * 1032u + 65536u)
+				cap = in_len * 1032u + 65536u;
 		}
 		if (z->res.status == B2I_S_BUF_ERROR && !final && known <= 0) {
 			want = in_len * 2 > want ? in_len * 2 : want * 2;   /* the stream is longer: get more input */

@@ -71,11 +71,16 @@ b200_ctx_release(b2i_ctx *c, int healthy)
 		b2i_ctx_destroy(c);
 }
 
-/* ---- pinned output buffers ---------------------------------------------------- */
-#define BUF_MAX    4
+/* ---- pinned output buffers ----------------------------------------------------
+ * Sizes are rounded to powers of two (256 KiB at least) so that a run of archives of
+ * similar size shares one buffer; when the shelf is full the SMALLEST buffers make
+ * room - a process that alternates small and large archives keeps the large one,
+ * which is the one that is expensive to pin again. */
+#define BUF_MAX    8
+#define BUF_MIN    ((size_t)256 << 10)
 #define BUF_KEEP   ((size_t)2 << 30)     /* total bytes kept idle at most */
 
-static struct { void *p; size_t cap; } bufs[BUF_MAX];
+static struct { void *p; size_t cap; } bufs[BUF_MAX + 1];
 static int bufs_n;
 
 void *
@@ -83,6 +88,7 @@ b200_buf_acquire(size_t need, size_t *cap)
 {
 	void *p = NULL;
 	int best = -1;
+	size_t want = BUF_MIN;
 
 	pthread_mutex_lock(&pool_lock);
 	for (int i = 0; i < bufs_n; i++)
@@ -96,8 +102,11 @@ b200_buf_acquire(size_t need, size_t *cap)
 	pthread_mutex_unlock(&pool_lock);
 	if (p != NULL)
 		return (p);
-	/* some headroom, so that a slightly larger archive next time still fits */
-	*cap = need + need / 8 + 4096;
+	while (want < need && want < ((size_t)1 << 30))
+		want <<= 1;
+	if (want < need)                      /* beyond 1 GiB: an eighth of headroom */
+		want = need + need / 8;
+	*cap = want;
 	if ((p = b2i_host_alloc(*cap)) == NULL) {
 		*cap = need;
 		p = b2i_host_alloc(need);
@@ -108,20 +117,52 @@ b200_buf_acquire(size_t need, size_t *cap)
 void
 b200_buf_release(void *p, size_t cap)
 {
+	void *drop[BUF_MAX + 1];
+	int ndrop = 0;
 	size_t idle = 0;
 
 	if (p == NULL)
 		return;
 	pthread_mutex_lock(&pool_lock);
+	bufs[bufs_n].p = p;                   /* the array has one slot more than the shelf */
+	bufs[bufs_n].cap = cap;
+	bufs_n++;
 	for (int i = 0; i < bufs_n; i++)
 		idle += bufs[i].cap;
-	if (bufs_n < BUF_MAX && idle + cap <= BUF_KEEP) {
-		bufs[bufs_n].p = p;
-		bufs[bufs_n].cap = cap;
-		bufs_n++;
-		p = NULL;
+	while (bufs_n > BUF_MAX || (bufs_n > 0 && idle > BUF_KEEP)) {
+		int s = 0;                    /* the smallest goes first */
+		for (int i = 1; i < bufs_n; i++)
+			if (bufs[i].cap < bufs[s].cap)
+				s = i;
+		idle -= bufs[s].cap;
+		drop[ndrop++] = bufs[s].p;
+		bufs[s] = bufs[--bufs_n];
 	}
 	pthread_mutex_unlock(&pool_lock);
-	if (p != NULL)
-		b2i_host_free(p);
+	for (int i = 0; i < ndrop; i++)
+		b2i_host_free(drop[i]);
+}
+
+/* the same shelf for callers that do not keep the capacity: it rides in front of the bytes */
+#define BUF_HDR 64
+
+void *
+b200_buf_acquire_tagged(size_t need)
+{
+	size_t cap;
+	unsigned char *p = b200_buf_acquire(need + BUF_HDR, &cap);
+
+	if (p == NULL)
+		return (NULL);
+	*(size_t *)(void *)p = cap;
+	return (p + BUF_HDR);
+}
+
+void
+b200_buf_release_tagged(void *q)
+{
+	if (q != NULL) {
+		unsigned char *p = (unsigned char *)q - BUF_HDR;
+		b200_buf_release(p, *(size_t *)(void *)p);
+	}
 }

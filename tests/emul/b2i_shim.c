@@ -30,7 +30,7 @@ int b2i_ctx_create(int device, void *cuda_stream, b2i_ctx **out)
 }
 void b2i_ctx_destroy(b2i_ctx *c) { free(c); }
 const char *b2i_last_error(const b2i_ctx *c) { (void)c; return "shim"; }
-void *b2i_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void *b2i_host_alloc(size_t bytes) { if (getenv("B2I_SHIM_STATS") && bytes > (32u << 20)) fprintf(stderr, "shim: host_alloc %zu\n", bytes); return malloc(bytes ? bytes : 1); }
 void b2i_host_free(void *p) { free(p); }
 void b2i_free(void *p) { free(p); }
 
