@@ -73,6 +73,7 @@ struct b2i_ctx {
 	                                           slice's long CTAs never queue behind another slice's */
 	cudaEvent_t ev_free;
 	bool pipe_ready;
+	size_t high_in, high_out, high_arena, high_crc, high_stage;   /* largest staging requests so far (ensure_dev) */
 	b2i_job jobs[B2I_MAX_JOBS];     /* host-buffer decodes in flight (b2i_submit / b2i_wait) */
 	char err[256];
 };
@@ -598,9 +599,17 @@ extern "C" void b2i_plan_destroy(b2i_plan *p)
 
 /* ---- host-buffer path --------------------------------------------------------- */
 
-static int ensure_dev(b2i_ctx *c, uint8_t **buf, size_t *cap, size_t need)
+/* Growing a job's device staging frees the old block, and cudaFree waits for EVERYTHING in
+ * flight on the device - with other jobs running that stalls the submitting thread for
+ * their whole duration (3 ms measured inside the streaming engine, where the job slots
+ * meet windows of different sizes in a different order every pass).  So a block that has
+ * to grow grows to the largest request the context has seen (*high), and every slot
+ * settles after at most one reallocation. */
+static int ensure_dev(b2i_ctx *c, uint8_t **buf, size_t *cap, size_t need, size_t *high)
 {
 	need = align_up(need, 16) + 16;
+	if (need > *high)
+		*high = need;
 	if (*cap >= need)
 		return B2I_OK;
 	if (*buf) {
@@ -609,7 +618,7 @@ static int ensure_dev(b2i_ctx *c, uint8_t **buf, size_t *cap, size_t need)
 		*buf = NULL;
 		*cap = 0;
 	}
-	size_t want = std::max(need, *cap + *cap / 2);
+	size_t want = std::max(*high, *cap + *cap / 2);
 	if (cudaMalloc(buf, want) != cudaSuccess) {
 		if (cudaMalloc(buf, need) != cudaSuccess)
 			return fail(c, B2I_E_NOMEM, "device allocation of %zu bytes failed", need);
@@ -634,13 +643,15 @@ static int ensure_pipe(b2i_ctx *c)
 
 static int ensure_arena(b2i_ctx *c, b2i_job *J, size_t need)
 {
+	if (need > c->high_arena)
+		c->high_arena = need;
 	if (J->arena_cap >= need)
 		return B2I_OK;
 	cudaDeviceSynchronize();
 	cudaFree(J->arena_d);
 	cudaFreeHost(J->arena_h);
 	J->arena_d = NULL; J->arena_h = NULL; J->arena_cap = 0;
-	need += need / 2;
+	need = c->high_arena + c->high_arena / 2;          /* see ensure_dev */
 	if (cudaMalloc(&J->arena_d, need) != cudaSuccess ||
 	    cudaHostAlloc((void **)&J->arena_h, need, cudaHostAllocDefault) != cudaSuccess)
 		return fail(c, B2I_E_NOMEM, "plan arena of %zu bytes", need);
@@ -715,9 +726,9 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 		*job = J;
 		return B2I_OK;
 	}
-	if ((rc = ensure_dev(c, &J->d_in, &J->d_in_cap, in_bytes)) != B2I_OK)
+	if ((rc = ensure_dev(c, &J->d_in, &J->d_in_cap, in_bytes, &c->high_in)) != B2I_OK)
 		return rc;
-	if ((rc = ensure_dev(c, &J->d_out, &J->d_out_cap, out_bytes)) != B2I_OK)
+	if ((rc = ensure_dev(c, &J->d_out, &J->d_out_cap, out_bytes, &c->high_out)) != B2I_OK)
 		return rc;
 
 	/* slices: contiguous descriptor ranges of about equal csize + usize */
@@ -806,6 +817,9 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 				J->h_stage = NULL;
 				J->h_stage_cap = 0;
 				size_t want = in_bytes + in_bytes / 4 + 64;
+				if (want > c->high_stage)
+					c->high_stage = want;
+				want = c->high_stage;          /* see ensure_dev */
 				if (cudaHostAlloc((void **)&J->h_stage, want, cudaHostAllocDefault) == cudaSuccess)
 					J->h_stage_cap = want;
 				else
@@ -1059,7 +1073,7 @@ extern "C" int b2i_crc32(b2i_ctx *c, uint32_t crc, const void *host_buf, size_t 
 		return B2I_OK;
 	}
 	CU(c, cudaSetDevice(c->device));
-	int rc = ensure_dev(c, &c->d_in, &c->d_in_cap, len);
+	int rc = ensure_dev(c, &c->d_in, &c->d_in_cap, len, &c->high_crc);
 	if (rc != B2I_OK)
 		return rc;
 	CU(c, cudaMemcpyAsync(c->d_in, host_buf, len, cudaMemcpyHostToDevice, c->stream));

@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -51,7 +52,10 @@ struct PinnedPool {
 	struct Buf { void *p; size_t cap; };
 	std::vector<Buf> free_;
 	size_t cached = 0;
-	static constexpr size_t kMaxCached = (size_t)2 << 30;
+	/* idle bytes kept: one ring of the largest default windows (5 x 512 MiB out plus their
+	 * input, about 4 GiB for text) must fit, or every pass pins its buffers again - 0.3 s
+	 * per GiB, more than the decode (measured: config 4 at 3 GB/s instead of 14) */
+	size_t kMaxCached = getenv("B2I_PINNED_CACHE_MB") ? (size_t)atol(getenv("B2I_PINNED_CACHE_MB")) << 20 : (size_t)5 << 30;
 
 	void *get(size_t need, size_t *cap)
 	{
@@ -216,6 +220,15 @@ void b2i_parallel_copy(void *dst, const void *src, size_t len)
 }
 
 struct b2i_pipe {
+	/* B2I_PIPE_TRACE=1: one line per window event on stderr, microseconds since open */
+	bool trace = getenv("B2I_PIPE_TRACE") != NULL;
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	void note(const char *what, size_t k) const
+	{
+		if (trace)
+			fprintf(stderr, "B2I_PIPE %9.1f us  window %3zu  %s\n",
+			    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(), k, what);
+	}
 	std::vector<b2i_ctx *> ctxs;
 	const uint8_t *mem = NULL;
 	uint64_t mem_size = 0;
@@ -238,6 +251,7 @@ struct b2i_pipe {
 	char err[256] = {0};
 	uint64_t stat_windows = 0, stat_fill_ns = 0;
 	size_t max_jobs = 4;         /* device passes in flight per GPU */
+	size_t window_out = 0;       /* output bytes a window is cut at */
 
 	size_t window_of(size_t idx) const
 	{
@@ -264,7 +278,10 @@ static void pipe_fail(b2i_pipe *p, int code, const char *fmt, ...)
 
 static bool slot_buffers(b2i_pipe *p, Slot &s, const Window &w, bool need_in)
 {
-	const size_t in_need = (size_t)(w.in_hi - w.in_lo) + 64;
+	/* input spans differ from window to window with the compression ratio: sizes are rounded
+	 * up to a coarse step so that a slot does not trade its buffer for a slightly larger one */
+	const size_t step = std::max<size_t>((size_t)1 << 20, align_up(p->window_out / 8, (size_t)1 << 20));
+	const size_t in_need = align_up((size_t)(w.in_hi - w.in_lo) + 64, step);
 	if (need_in && s.h_in_cap < in_need) {
 		g_pinned.put(s.h_in, s.h_in_cap);
 		s.h_in = (uint8_t *)g_pinned.get(in_need, &s.h_in_cap);
@@ -319,6 +336,7 @@ static void worker_main(b2i_pipe *p, size_t dev)
 				s.state = FILLING;
 				s.window = k;
 				lk.unlock();
+				p->note("stage", k);
 				bool ok = slot_buffers(p, s, w, !p->mem_pinned);
 				if (ok) {
 					if (p->mem_pinned) {
@@ -336,6 +354,7 @@ static void worker_main(b2i_pipe *p, size_t dev)
 			}
 			if (s.window == k && s.state == FILLED && p->error == B2I_OK) {
 				lk.unlock();
+				p->note("submit", k);
 				b2i_job *job = NULL;
 				int rc = b2i_submit(ctx, s.in_base, (size_t)(w.in_hi - w.in_lo), s.descs.data(), w.count,
 				    s.h_out, w.out_bytes, &job);
@@ -360,6 +379,7 @@ static void worker_main(b2i_pipe *p, size_t dev)
 			Slot &s = p->slots[pd.k % p->slots.size()];
 			lk.unlock();
 			int rc = b2i_wait(pd.job, s.res.data());
+			p->note("done", pd.k);
 			lk.lock();
 			if (rc != B2I_OK)
 				pipe_fail(p, rc, "window %zu: %s", pd.k, b2i_last_error(ctx));
@@ -405,10 +425,21 @@ extern "C" int b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, ui
 		 * ring - which costs seconds to pin per GiB in a cold process - small. */
 		window_out = (size_t)std::min<uint64_t>((uint64_t)256 << 20,
 		    std::max<uint64_t>((uint64_t)16 << 20, total / (4u * (unsigned)nctx)));
+		/* A window is done when its LONGEST stream is (a 16 MiB entry takes 40 ms on its CTA,
+		 * whatever else the window holds), so archives with large entries need more bytes in
+		 * flight to keep the device busy: 32 largest-entries per window, up to 512 MiB
+		 * (config 4 through the public API: 12.4 GB/s with 256 MiB windows, 21.0 with 512). */
+		uint64_t largest = 0;
+		for (size_t i = 0; i < n; i++)
+			largest = std::max<uint64_t>(largest, descs[i].out_cap);
+		if (largest >= ((uint64_t)1 << 20))
+			window_out = (size_t)std::max<uint64_t>(window_out,
+			    std::min<uint64_t>({(uint64_t)512 << 20, 32 * largest, std::max<uint64_t>(total / 2, (uint64_t)16 << 20)}));
 		if (fill != NULL && window_out > ((size_t)64 << 20))
 			window_out = (size_t)64 << 20;
 	}
-	size_t first_out = opts && opts->first_window_out_bytes ? opts->first_window_out_bytes : window_out / 4;
+	size_t first_out = opts && opts->first_window_out_bytes ? opts->first_window_out_bytes
+	    : std::min<size_t>(window_out / 4, (size_t)16 << 20);
 	int depth = opts && opts->windows_per_device > 0 ? opts->windows_per_device : 5;
 	if (const char *ev = getenv("B2I_PIPE_WINDOW_MB"))
 		window_out = (size_t)std::max(1, atoi(ev)) << 20, first_out = window_out / 4;
@@ -425,6 +456,7 @@ extern "C" int b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, ui
 		return B2I_E_NOMEM;
 	p->ctxs.assign(ctxs, ctxs + nctx);
 	p->max_jobs = jobs;
+	p->window_out = window_out;
 	p->mem = (const uint8_t *)mem;
 	p->mem_size = mem_size;
 	p->fill = fill;
@@ -551,6 +583,8 @@ extern "C" int b2i_pipe_get(b2i_pipe *p, size_t idx, const void **out_data, cons
 			continue;
 		p->cv_ready.wait(lk);
 	}
+	if (idx == p->win[wi].first)
+		p->note("handed out", wi);
 	/* keep the ring full while the caller chews on this window */
 	while (fill_one(p, lk))
 		;

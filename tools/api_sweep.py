@@ -6,8 +6,9 @@ name = sys.argv[1] if len(sys.argv) > 1 else "zip64k"
 archive, kind = bench.build_workload(name, 0, bench.CONFIGS[name][3])
 path = "/dev/shm/b2i_sweep.bin"
 open(path, "wb").write(archive)
-exe = os.path.join("libarchive_b200", "api_bench")
-for env in ({}, {"B2I_PIPE_JOBS": "4", "B2I_PIPE_DEPTH": "5"}, {"B2I_PIPE_JOBS": "4", "B2I_PIPE_DEPTH": "5", "B2I_PIPE_WINDOW_MB": "64", "B2I_PIPE_FIRST_MB": "16"},
+exe = os.environ.get("API_BENCH", os.path.join("libarchive_b200", "api_bench"))
+SWEEP = json.loads(os.environ["SWEEP"]) if os.environ.get("SWEEP") else None
+for env in SWEEP or ({}, {"B2I_PIPE_JOBS": "4", "B2I_PIPE_DEPTH": "5"}, {"B2I_PIPE_JOBS": "4", "B2I_PIPE_DEPTH": "5", "B2I_PIPE_WINDOW_MB": "64", "B2I_PIPE_FIRST_MB": "16"},
             {"B2I_PIPE_JOBS": "4", "B2I_PIPE_DEPTH": "5", "B2I_PIPE_WINDOW_MB": "64", "B2I_PIPE_FIRST_MB": "64"},
             {"B2I_PIPE_JOBS": "4", "B2I_PIPE_DEPTH": "6", "B2I_PIPE_WINDOW_MB": "32", "B2I_PIPE_FIRST_MB": "16"},
             {"B2I_PIPE_JOBS": "3", "B2I_PIPE_DEPTH": "4", "B2I_PIPE_WINDOW_MB": "96", "B2I_PIPE_FIRST_MB": "32"},
