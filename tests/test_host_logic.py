@@ -174,3 +174,19 @@ def test_zip_index_through_fetch_callback_equals_memory_walk():
     assert capi.lib().b2i_zip_probe_tail(junk[-16384:], 16384, len(junk)) == 0
     with pytest.raises(capi.B2IError):
         capi.zip_index_via_fetch(junk)
+
+
+def test_plugin_pinned_buffer_shelf(tmp_path):
+    """The plugins' shelf of pinned output buffers (csrc/plugin/b200_ctx_pool.c): size
+    classes, reuse, smallest-first eviction, bounded idle total - compiled with malloc in
+    place of cudaHostAlloc (tests/csrc/buf_pool_test.c)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "buf_pool_test")
+    subprocess.run(["gcc", "-O1", "-Wall", "-I" + os.path.join(root, "include"),
+                    "-I" + os.path.join(root, "libarchive_b200", "csrc", "plugin"), "-o", exe,
+                    os.path.join(root, "tests", "csrc", "buf_pool_test.c"),
+                    os.path.join(root, "libarchive_b200", "csrc", "plugin", "b200_ctx_pool.c"), "-lpthread"],
+                   check=True, timeout=120)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
