@@ -171,6 +171,12 @@ int  b2i_wait(b2i_job *job, b2i_stream_result *res /* n entries */);
 /* blocks until the job's input has been copied to the device: host_in may then be
  * released (a read filter consumes its upstream bytes) while the job decodes on */
 int  b2i_job_wait_input(b2i_job *job);
+/* Where the library keeps its own pinned copy of the job's input (pageable inputs of a few
+ * MiB and more are staged), or NULL if it reads host_in directly.  base + in_off holds the
+ * bytes of every stream of the job.  Ask before b2i_wait; the bytes stay until the next
+ * b2i_submit on the context.  (The gzip filter releases its upstream bytes after
+ * b2i_job_wait_input and comes back here for the one member whose trailer lied.) */
+const void *b2i_job_staged_input(const b2i_job *job);
 
 /* The same over several GPUs of one box: the batch is partitioned on the
  * host (b2i_partition_contiguous, or b2i_partition_lpt when a few streams dominate),

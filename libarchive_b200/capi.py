@@ -71,6 +71,7 @@ EXPORTS = [
     "b2i_gzip_scan_bgzf", "b2i_free", "b2i_partition_contiguous", "b2i_partition_lpt",
     "b2i_decode_host_multi", "b2i_pipe_open", "b2i_pipe_get", "b2i_pipe_release", "b2i_pipe_window_count",
     "b2i_pipe_error", "b2i_pipe_close", "b2i_zip_index_build_cb", "b2i_zip_probe_tail", "b2i_ctx_device", "b2i_job_wait_input",
+    "b2i_job_staged_input",
 ]
 
 _lib = None
@@ -115,6 +116,8 @@ def lib():
     L.b2i_submit.argtypes = [vp, vp, sz, C.POINTER(StreamDesc), sz, vp, sz, C.POINTER(vp)]
     L.b2i_wait.argtypes = [vp, C.POINTER(StreamResult)]
     L.b2i_job_wait_input.argtypes = [vp]
+    L.b2i_job_staged_input.argtypes = [vp]
+    L.b2i_job_staged_input.restype = vp
     L.b2i_crc32.argtypes = [vp, u32, vp, sz, C.POINTER(u32)]
     L.b2i_crc32_device.argtypes = [vp, u32, vp, sz, C.POINTER(u32)]
     L.b2i_crc32_combine.argtypes = [u32, u32, u64]

@@ -44,6 +44,7 @@ struct b2i_job {
 	uint8_t *d_in;  size_t d_in_cap;
 	uint8_t *d_out; size_t d_out_cap;
 	uint8_t *h_stage; size_t h_stage_cap;   /* pinned staging for pageable input */
+	bool staged;                            /* this job reads its input from h_stage */
 	uint8_t *arena_d; uint8_t *arena_h; size_t arena_cap;
 	cudaEvent_t ev_in[B2I_PIPE_SLICES], ev_k[B2I_PIPE_SLICES], ev_done;
 	b2i_plan *plans[B2I_PIPE_SLICES];
@@ -706,6 +707,7 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 	J->ctx = c;
 	J->n = n;
 	J->K = 0;
+	J->staged = false;
 	for (size_t s = 0; s < B2I_PIPE_SLICES; s++)
 		J->plans[s] = NULL;
 	CU(c, cudaSetDevice(c->device));
@@ -826,6 +828,7 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 					cudaGetLastError();
 			}
 			stage = J->h_stage;          /* NULL: no pinned memory to be had, the driver copies */
+			J->staged = stage != NULL;
 		}
 	}
 	b2i_plan **plans = J->plans;
@@ -938,6 +941,11 @@ extern "C" int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes,
 	}
 	*job = J;
 	return B2I_OK;
+}
+
+extern "C" const void *b2i_job_staged_input(const b2i_job *J)
+{
+	return (J != NULL && J->busy && J->staged) ? J->h_stage : NULL;
 }
 
 /* the job's input has been copied to the device: host_in may be reused or released */

@@ -76,6 +76,10 @@ struct gz_b200 {
 		size_t          cap, n;
 		b2i_stream_desc   *d;
 		b2i_stream_result *r;
+		const unsigned char *src;     /* the window's input after upstream has consumed it: the
+		                               * library's staged copy, or `keep` below */
+		unsigned char  *keep;
+		size_t          keep_cap;
 	} q[GZ_JOBS];
 	int             qh, qn;       /* head and length of the queue (slots are used round-robin) */
 	size_t          windows;      /* BGZF windows submitted so far */
@@ -83,6 +87,7 @@ struct gz_b200 {
 
 static int	bgzf_submit(struct archive_read_filter *, const unsigned char *, const b2i_gzip_member *, size_t);
 static int	bgzf_collect(struct archive_read_filter *);
+static int	bgzf_redo_window(struct gz_b200 *, struct gz_job *);
 
 static int	gz_bid(struct archive_read_filter_bidder *, struct archive_read_filter *);
 static int	gz_init(struct archive_read_filter *);
@@ -273,8 +278,24 @@ bgzf_submit(struct archive_read_filter *self, const unsigned char *p, const b2i_
 	}
 	j->n = m_used;
 	rc = b2i_submit(g->ctx, p, in_used, j->d, m_used, j->buf + OUT_BLOCK, out, &j->job);
-	if (rc == B2I_OK)
+	if (rc == B2I_OK) {
+		/* A member whose trailer understates its size has to be decoded again with room
+		 * (bgzf_collect), after upstream has given its bytes away: large windows are
+		 * found in the library's pinned staging, small ones are kept here. */
+		j->src = b2i_job_staged_input(j->job);
+		if (j->src == NULL && !g->verify) {
+			if (j->keep_cap < in_used) {
+				free(j->keep);
+				j->keep = malloc(in_used);
+				j->keep_cap = j->keep ? in_used : 0;
+			}
+			if (j->keep != NULL) {
+				memcpy(j->keep, p, in_used);
+				j->src = j->keep;
+			}
+		}
 		rc = b2i_job_wait_input(j->job);
+	}
 	if (rc != B2I_OK) {
 		g->ctx_bad = (rc == B2I_E_CUDA);
 		return (fatal(self, g, b2i_last_error(g->ctx)));
@@ -310,6 +331,65 @@ bgzf_top_up(struct archive_read_filter *self)
 	return (ARCHIVE_OK);
 }
 
+/* Members of a finished window overflowed the size their trailers announced: decode those
+ * again alone with room (deflate cannot expand by more than 1032:1) and lay the window out
+ * anew, every member at an offset that fits what it really produced. */
+static int
+bgzf_redo_window(struct gz_b200 *g, struct gz_job *j)
+{
+	unsigned char **alt = calloc(j->n, sizeof(*alt)), *nb;
+	size_t i, total = 0, ncap = 0, o = 0;
+	int rc = ARCHIVE_OK;
+
+	if (alt == NULL)
+		return (ARCHIVE_FATAL);
+	for (i = 0; i < j->n; i++) {
+		b2i_stream_result *r = &j->r[i];
+		const size_t most = (size_t)j->d[i].in_len * 1032u + 65536u;
+		size_t cap = (size_t)j->d[i].out_cap;
+
+		while (r->status == B2I_S_OUT_OVERFLOW && cap < most) {
+			b2i_stream_desc d = j->d[i];
+			cap = cap < 16384 ? 65536 : cap * 4;
+			if (cap > most)
+				cap = most;
+			b200_buf_release_tagged(alt[i]);
+			if ((alt[i] = b200_buf_acquire_tagged(cap + 16)) == NULL) {
+				rc = ARCHIVE_FATAL;
+				break;
+			}
+			d.in_off = 0;
+			d.out_off = 0;
+			d.out_cap = cap;
+			if (b2i_decode_host(g->ctx, j->src + j->d[i].in_off, (size_t)d.in_len, &d, 1, alt[i], cap, r) != B2I_OK) {
+				r->status = B2I_S_OUT_OVERFLOW;      /* reported as a failed member, nothing of it served */
+				r->out_bytes = 0;
+				break;
+			}
+		}
+		total += ((size_t)r->out_bytes + 15) & ~(size_t)15;
+	}
+	nb = rc == ARCHIVE_OK ? b200_buf_acquire(OUT_BLOCK + total + 16, &ncap) : NULL;
+	if (nb == NULL)
+		rc = ARCHIVE_FATAL;
+	for (i = 0; i < j->n; i++) {
+		if (rc == ARCHIVE_OK) {
+			memcpy(nb + OUT_BLOCK + o, alt[i] ? alt[i] : j->buf + OUT_BLOCK + j->d[i].out_off,
+			    (size_t)j->r[i].out_bytes);
+			j->d[i].out_off = o;
+			o += ((size_t)j->r[i].out_bytes + 15) & ~(size_t)15;
+		}
+		b200_buf_release_tagged(alt[i]);
+	}
+	free(alt);
+	if (rc == ARCHIVE_OK) {
+		b200_buf_release(j->buf, j->cap);
+		j->buf = nb;
+		j->cap = ncap;
+	}
+	return (rc);
+}
+
 /* wait for the oldest window in flight, make its buffer the one being served (the few bytes
  * still pending move in front of it) and queue the windows after it */
 static int
@@ -329,6 +409,17 @@ bgzf_collect(struct archive_read_filter *self)
 		g->ctx_bad = (rc == B2I_E_CUDA);
 		return (fatal(self, g, b2i_last_error(g->ctx)));
 	}
+	/* The reference never looks at ISIZE (gzip.c:427-431, "XXX TODO: Verify the length and
+	 * CRC"): a member that produced more than its trailer says is decoded again with
+	 * room, and the window is put together anew (unless verification was asked for). */
+	if (!g->verify && j->src != NULL)
+		for (i = 0; i < j->n; i++)
+			if (j->r[i].status == B2I_S_OUT_OVERFLOW) {
+				if ((rc = bgzf_redo_window(g, j)) != ARCHIVE_OK)
+					return (fatal(self, g, "Can't allocate data for gzip decompression"));
+				dst = j->buf + OUT_BLOCK;
+				break;
+			}
 	/* members are served back to back: close the 16-byte alignment gaps */
 	for (i = 0; i < j->n; i++) {
 		const b2i_stream_desc *d = &j->d[i];
@@ -591,6 +682,7 @@ gz_close(struct archive_read_filter *self)
 		b200_buf_release(g->q[i].buf, g->q[i].cap);
 		free(g->q[i].d);
 		free(g->q[i].r);
+		free(g->q[i].keep);
 	}
 	b200_buf_release(g->out, g->out_cap);
 	b200_ctx_release(g->ctx, !g->ctx_bad);

@@ -20,7 +20,7 @@
 static long g_calls, g_streams;
 static void shim_report(void) { if (getenv("B2I_SHIM_STATS")) fprintf(stderr, "shim: %ld decode calls, %ld streams\n", g_calls, g_streams); }
 
-struct b2i_ctx { int dummy; };
+struct b2i_ctx { void *keep; };   /* the last finished job's input copy (b2i_job_staged_input) */
 
 int b2i_ctx_create(int device, void *cuda_stream, b2i_ctx **out)
 {
@@ -28,7 +28,7 @@ int b2i_ctx_create(int device, void *cuda_stream, b2i_ctx **out)
 	*out = calloc(1, sizeof(struct b2i_ctx));
 	return *out ? B2I_OK : B2I_E_NOMEM;
 }
-void b2i_ctx_destroy(b2i_ctx *c) { free(c); }
+void b2i_ctx_destroy(b2i_ctx *c) { if (c) free(c->keep); free(c); }
 const char *b2i_last_error(const b2i_ctx *c) { (void)c; return "shim"; }
 void *b2i_host_alloc(size_t bytes) { if (getenv("B2I_SHIM_STATS") && bytes > (32u << 20)) fprintf(stderr, "shim: host_alloc %zu\n", bytes); return malloc(bytes ? bytes : 1); }
 void b2i_host_free(void *p) { free(p); }
@@ -72,9 +72,16 @@ int b2i_submit(b2i_ctx *c, const void *host_in, size_t in_bytes, const b2i_strea
 	struct b2i_job *j = calloc(1, sizeof(*j));
 	if (j == NULL)
 		return B2I_E_NOMEM;
+	free(c->keep);                 /* "until the next b2i_submit on the context" */
+	c->keep = NULL;
 	j->c = c; j->in = host_in; j->in_bytes = in_bytes; j->n = n; j->out = host_out; j->out_bytes = out_bytes;
 	j->descs = malloc((n ? n : 1) * sizeof(*descs));
 	if (n) memcpy(j->descs, descs, n * sizeof(*descs));
+	/* like the library, inputs of 4 MiB and more are "staged" at once (b2i_job_staged_input) */
+	if (n && in_bytes >= ((size_t)4 << 20) && (j->owned = malloc(in_bytes)) != NULL) {
+		memcpy(j->owned, host_in, in_bytes);
+		j->in = j->owned;
+	}
 	*job = j;
 	return B2I_OK;
 }
@@ -92,11 +99,14 @@ int b2i_job_wait_input(b2i_job *j)
 	return B2I_OK;
 }
 
+const void *b2i_job_staged_input(const b2i_job *j) { return j->owned; }
+
 int b2i_wait(b2i_job *j, b2i_stream_result *res)
 {
 	int rc = j->n ? b2i_decode_host(j->c, j->in, j->in_bytes, j->descs, j->n, j->out, j->out_bytes, res) : B2I_OK;
 	free(j->descs);
-	free(j->owned);
+	free(j->c->keep);
+	j->c->keep = j->owned;
 	free(j);
 	return rc;
 }

@@ -182,6 +182,17 @@ def test_bgzf_and_plain_gzip_identical_reports():
         assert rb[0].get("rd", rb[0].get("open")) == -30
 
 
+def test_bgzf_members_with_wrong_isize_identical_reports():
+    """ISIZE too small / too large / zero in some BGZF trailers (data intact): the reference
+    ignores the field; the drop-in decodes such a member again with room."""
+    need_dropin()
+    if not ob.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import stream_cases
+    stream_cases.check_bgzf_trailers(ob.REF_EXTRACT, DROPIN, 300)
+    stream_cases.check_bgzf_trailers(ob.REF_EXTRACT, DROPIN, 1500)
+
+
 def test_streaming_reader_identical_reports():
     """Non-seekable input: the streaming ZIP reader (local headers, data descriptors) of the
     drop-in against the reference's, on generated archives with good and bad entries."""
