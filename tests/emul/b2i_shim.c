@@ -45,9 +45,9 @@ int b2i_decode_host(b2i_ctx *c, const void *host_in, size_t in_bytes, const b2i_
     size_t n, void *host_out, size_t out_bytes, b2i_stream_result *results)
 {
 	(void)c;
-	if (g_calls++ == 0)
+	if (__atomic_fetch_add(&g_calls, 1, __ATOMIC_RELAXED) == 0)      /* several worker threads call in */
 		atexit(shim_report);
-	g_streams += (long)n;
+	__atomic_fetch_add(&g_streams, (long)n, __ATOMIC_RELAXED);
 	_Static_assert(sizeof(orc_desc) == sizeof(b2i_stream_desc), "descriptor layouts differ");
 	_Static_assert(sizeof(orc_stream_result) == sizeof(b2i_stream_result), "result layouts differ");
 	return orc_decode_batch(host_in, in_bytes, (const orc_desc *)descs, n, host_out, out_bytes,
