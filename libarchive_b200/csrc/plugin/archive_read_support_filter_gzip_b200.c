@@ -409,7 +409,7 @@ bgzf_collect(struct archive_read_filter *self)
 		g->ctx_bad = (rc == B2I_E_CUDA);
 		return (fatal(self, g, b2i_last_error(g->ctx)));
 	}
-	/* The reference never looks at ISIZE (gzip.c:427-431, "XXX TODO: Verify the length and
+	/* The reference never looks at ISIZE (gzip.c:423, "XXX TODO: Verify the length and
 	 * CRC"): a member that produced more than its trailer says is decoded again with
 	 * room, and the window is put together anew (unless verification was asked for). */
 	if (!g->verify && j->src != NULL)

@@ -112,7 +112,7 @@ def check_fixtures(ref_binary, new_binary, fixture_dir, raw_of, refused=()):
 def bgzf_with_lying_trailers(n_members=300, member=60000, seed=7):
     """A BGZF chain whose data is intact but whose ISIZE fields are not: too small (a few
     members, one of them by a lot), too large, zero.  The reference never looks at ISIZE
-    (archive_read_support_filter_gzip.c:427-431), so it decodes all of it."""
+    (archive_read_support_filter_gzip.c:423), so it decodes all of it."""
     import struct
     parts = synth.split_text(n_members * member, member, seed)
     blob = bytearray(synth.make_bgzf(parts))
