@@ -435,8 +435,15 @@ extern "C" int b2i_pipe_open(b2i_ctx *const *ctxs, int nctx, const void *mem, ui
 		if (largest >= ((uint64_t)1 << 20))
 			window_out = (size_t)std::max<uint64_t>(window_out,
 			    std::min<uint64_t>({(uint64_t)512 << 20, 32 * largest, std::max<uint64_t>(total / 2, (uint64_t)16 << 20)}));
-		if (fill != NULL && window_out > ((size_t)64 << 20))
-			window_out = (size_t)64 << 20;
+		/* callback sources keep the ring small (64 MiB windows) unless the entries are large:
+		 * 16 largest-entries per window, 256 MiB at most (config 4 from a file: 3 GB/s with
+		 * 64 MiB windows, which hold four 16 MiB entries each) */
+		if (fill != NULL) {
+			const size_t small = (size_t)std::max<uint64_t>((uint64_t)64 << 20,
+			    std::min<uint64_t>((uint64_t)256 << 20, 16 * largest));
+			if (window_out > small)
+				window_out = small;
+		}
 	}
 	size_t first_out = opts && opts->first_window_out_bytes ? opts->first_window_out_bytes
 	    : std::min<size_t>(window_out / 4, (size_t)16 << 20);

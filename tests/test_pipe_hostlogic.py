@@ -134,9 +134,10 @@ def test_default_window_sizes(H):
     assert windows([65536] * 4096, mem=mem, mem_size=4096) == 1 + -(-(256 - 16) // 64)
     # 2 GiB with 16 MiB entries among small ones: 512 MiB windows (32 x the largest)
     assert windows([16 * MiB] * 8 + [MiB] * 1920, mem=mem, mem_size=4096) == 1 + -(-(2048 - 16) // 512)
-    # the same through a callback source: 64 MiB windows
-    n = windows([16 * MiB] * 8 + [MiB] * 1920, fill=lambda u, o, l, d: 0)
-    assert 30 <= n <= 40
+    # the same through a callback source: 256 MiB windows (16 x the largest); 64 MiB when the
+    # entries are small
+    assert windows([16 * MiB] * 8 + [MiB] * 1920, fill=lambda u, o, l, d: 0) == 1 + -(-(2048 - 16) // 256)
+    assert windows([MiB] * 2048, fill=lambda u, o, l, d: 0) == 1 + -(-(2048 - 16) // 64)
     # small archive: one 16 MiB window minimum -> first 4 MiB
     assert windows([65536] * 128, mem=mem, mem_size=4096) == 2
     c.close()
