@@ -82,3 +82,31 @@ def test_reference_fixtures_full_metadata_match_reference():
     expected = json.load(open(os.path.join(gold, "ref_expected.json")))
     stream_cases.check_fixtures(ref, new, os.path.join(gold, "ref_fixtures"), {k: v["raw"] for k, v in expected.items()},
                                 refused=("test_read_format_zip_encryption_data.zip",))
+
+
+def test_handles_on_several_threads(tmp_path):
+    """Six threads, each with its own archive handle, read the same archive at the same time
+    (one-call path, streaming engine, two "devices", BGZF filter): every thread sees the same
+    bytes.  The ThreadSanitizer build of the same program (make -C tests/refsuite tsan) reports
+    no race in this repo's code."""
+    exe = os.path.join(NEWDIR, "mt_read_hostlogic")
+    if not os.path.exists(exe):
+        pytest.skip("tests/refsuite/_out/mt_read_hostlogic not built (needs /root/reference)")
+    sys.path.insert(0, ROOT)
+    import json
+    import zlib
+    from libarchive_b200 import synth
+    parts = synth.split_text(200 * 50000, 50000, 31)
+    z = tmp_path / "a.zip"
+    z.write_bytes(synth.make_zip([synth.ZipMember("e%03d" % i, p) for i, p in enumerate(parts)]))
+    g = tmp_path / "a.bgzf"
+    g.write_bytes(synth.make_bgzf(parts))
+    want = "%08x" % (zlib.crc32(b"".join(parts)) & 0xFFFFFFFF)
+    for path, extra, env in ((z, [], {}), (z, [], {"B2I_ZIP_PIPE": "1", "B2I_PIPE_WINDOW_MB": "1"}),
+                             (z, [], {"B2I_ZIP_PIPE": "1", "B2I_PIPE_WINDOW_MB": "1", "B2I_SHIM_GPUS": "2", "B2I_PLUGIN_GPUS": "2"}),
+                             (g, ["--raw"], {})):
+        r = subprocess.run([exe, str(path), "6", "2"] + extra, capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, (env, r.stdout, r.stderr[-500:])
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        assert j["bad_threads"] == 0 and j["bytes"] == 200 * 50000 and j["crc"] == want, (env, j)
