@@ -212,3 +212,26 @@ def test_reference_fixtures_full_metadata_identical():
     import stream_cases
     stream_cases.check_fixtures(ob.REF_EXTRACT, DROPIN, os.path.join(GOLD, "ref_fixtures"),
                                 {k: v["raw"] for k, v in EXPECTED.items()}, refused=tuple(REFUSED))
+
+
+def test_handles_on_several_threads(tmp_path):
+    """Six threads, each with its own archive handle, read the same archive through the drop-in
+    at the same time (tests/csrc/mt_read.c): one-call path or streaming engine as the size
+    decides, the engine forced with small windows, and the BGZF filter.  Every thread sees the
+    same bytes (context pool, pinned shelf, copy threads, five jobs per context under
+    concurrency)."""
+    exe = os.path.join(ROOT, "tests", "refsuite", "_out", "mt_read_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("tests/refsuite/_out/mt_read_dropin not built (needs /root/reference)")
+    parts = synth.split_text(600 * 50000, 50000, 31)
+    want = "%08x" % (zlib.crc32(b"".join(parts)) & 0xFFFFFFFF)
+    z = tmp_path / "a.zip"
+    z.write_bytes(synth.make_zip([synth.ZipMember("e%03d" % i, p) for i, p in enumerate(parts)]))
+    g = tmp_path / "a.bgzf"
+    g.write_bytes(synth.make_bgzf(parts))
+    for path, extra, env in ((z, [], {}), (z, [], {"B2I_ZIP_PIPE": "1", "B2I_PIPE_WINDOW_MB": "4"}), (g, ["--raw"], {})):
+        r = subprocess.run([exe, str(path), "6", "3"] + extra, capture_output=True, text=True, timeout=120,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, (env, r.stdout, r.stderr[-500:])
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        assert j["bad_threads"] == 0 and j["bytes"] == 600 * 50000 and j["crc"] == want, (env, j)
